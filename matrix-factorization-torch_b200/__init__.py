@@ -1,0 +1,56 @@
+"""xfmr_b200 — B200 (sm_100a) implementation of the query-by-item score path of ``xfmr_rec``.
+
+Importable as ``xfmr_b200`` (shim module at the repository root; this directory's name has hyphens).
+Public surface, mirroring the reference interfaces for this path:
+
+* the seven loss modules of ``xfmr_rec/losses.py`` + ``fused_losses`` (one contraction for any subset),
+* ``ItemProcessor`` / ``topk_search`` — exact top-k with the semantics of ``ItemProcessor.search``,
+* ``hash_embedding_gather`` / ``HashEmbeddingBag`` — the hashed-embedding feeder,
+* ``distributed`` — global negatives (training) and catalog sharding (retrieval).
+"""
+
+from . import distributed
+from ._lib import LIB_PATH, XbError, launch_count
+from .hashing import HashEmbeddingBag, hash_embedding_gather, hash_indices
+from .losses import (
+    ALL_LOSSES,
+    LOSS_CLASSES,
+    LOSS_SLOTS,
+    AlignmentContrastiveLoss,
+    AlignmentLoss,
+    ContrastiveLoss,
+    EmbeddingLoss,
+    InfomationNoiseContrastiveEstimationLoss,
+    MutualInformationNeuralEstimationLoss,
+    PairwiseHingeLoss,
+    PairwiseLogisticLoss,
+    fused_losses,
+)
+from .retrieval import TOP_K, ItemProcessor, build_pair_mask, topk_merge, topk_search
+
+__all__ = [
+    "ALL_LOSSES",
+    "LIB_PATH",
+    "LOSS_CLASSES",
+    "LOSS_SLOTS",
+    "TOP_K",
+    "AlignmentContrastiveLoss",
+    "AlignmentLoss",
+    "ContrastiveLoss",
+    "EmbeddingLoss",
+    "HashEmbeddingBag",
+    "InfomationNoiseContrastiveEstimationLoss",
+    "ItemProcessor",
+    "MutualInformationNeuralEstimationLoss",
+    "PairwiseHingeLoss",
+    "PairwiseLogisticLoss",
+    "XbError",
+    "build_pair_mask",
+    "distributed",
+    "fused_losses",
+    "hash_embedding_gather",
+    "hash_indices",
+    "launch_count",
+    "topk_merge",
+    "topk_search",
+]

@@ -1,0 +1,789 @@
+// extern "C" entry points of libxfmr_b200.so (declared in include/xfmr_b200.h): argument checking,
+// workspace carving, TMA descriptor construction and the kernel launch sequences.  No torch types,
+// no allocation, no host synchronisation.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/xfmr_b200.h"
+#include "aux_kernels.cuh"
+#include "sweep_launch.h"
+
+namespace xb {
+
+constexpr int NUM_SMS = 148;                // B200; the launch plan (and so the workspace) is fixed on it
+constexpr size_t SMEM_BUDGET = 232448;      // 227 KB opt-in dynamic shared memory per CTA
+
+thread_local std::string g_last_error = "";
+thread_local long long g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define XB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(XB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define XB_LAUNCHED()                                                                              \
+  do {                                                                                             \
+    ++g_launches;                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return fail(XB_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors.  libcuda is resolved at run time through the runtime API so that the library
+// (and `import` of the Python package) loads on a machine without a driver.
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 matrix [rows, row_elems] row-major; box = 64 columns x 128 rows, 128-byte swizzle, zero OOB fill.
+static int make_operand_map(CUtensorMap* map, const void* base, long long rows, long long row_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(XB_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_elems), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_elems) * 2};
+  cuuint32_t box[2] = {KBLK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(XB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch plan of one sweep: how the column tiles are split across CTAs and how deep the TMA ring is.
+// ------------------------------------------------------------------------------------------------
+struct SweepPlan {
+  int n_rblocks, n_ctiles, nchunks, tiles_per_cta, nstages;
+  size_t smem;
+  bool ok;
+};
+
+static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int cpar_floats) {
+  SweepPlan pl{};
+  pl.n_rblocks = cdiv(nR, BM);
+  pl.n_ctiles = cdiv(nC, BN);
+  int want = (2 * NUM_SMS) / (pl.n_rblocks > 0 ? pl.n_rblocks : 1);
+  if (want < 1) want = 1;
+  if (want > pl.n_ctiles) want = pl.n_ctiles;
+  if (want < 1) want = 1;
+  int per = cdiv(pl.n_ctiles, want);
+  const int min_per = pl.n_ctiles < 4 ? pl.n_ctiles : 4;
+  if (per < min_per) per = min_per;
+  if (per < 1) per = 1;
+  pl.tiles_per_cta = per;
+  pl.nchunks = pl.n_ctiles > 0 ? cdiv(pl.n_ctiles, per) : 1;
+  pl.ok = false;
+  for (int ns = MAX_STAGES; ns >= (has_g ? 2 : 1); --ns) {
+    const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, has_g, cpar_floats);
+    if (lay.total <= SMEM_BUDGET) {
+      pl.nstages = ns;
+      pl.smem = lay.total;
+      pl.ok = true;
+      break;
+    }
+  }
+  return pl;
+}
+
+static inline int mask_words_for(int ncols) { return 4 * cdiv(ncols, BN); }
+
+static inline int sweep_lm_from_mask(uint32_t loss_mask) {
+  int lm = 0;
+  if (loss_mask & ((1u << XB_LOSS_CONTRASTIVE) | (1u << XB_LOSS_ALIGNMENT_CONTRASTIVE))) lm |= LM_CONTR;
+  if (loss_mask & (1u << XB_LOSS_INFONCE)) lm |= LM_INFONCE;
+  if (loss_mask & (1u << XB_LOSS_MINE)) lm |= LM_MINE;
+  if (loss_mask & (1u << XB_LOSS_PAIRWISE_HINGE)) lm |= LM_HINGE;
+  if (loss_mask & (1u << XB_LOSS_PAIRWISE_LOGISTIC)) lm |= LM_LOGI;
+  if (lm != 0 && !lm_single(lm)) lm = LM_ALL;
+  return lm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pair mask
+// ------------------------------------------------------------------------------------------------
+struct PairMaskWs {
+  size_t keys_off, heads_off, next_off, total;
+  int tsize;
+};
+static PairMaskWs pair_mask_ws(int ncols) {
+  PairMaskWs w{};
+  int ts = 64;
+  while (ts < 2 * ncols) ts <<= 1;
+  w.tsize = ts;
+  size_t off = 0;
+  w.keys_off = off; off = align_up(off + sizeof(long long) * ts, 256);
+  w.heads_off = off; off = align_up(off + sizeof(int) * ts, 256);
+  w.next_off = off; off = align_up(off + sizeof(int) * (ncols > 0 ? ncols : 1), 256);
+  w.total = off;
+  return w;
+}
+
+static int build_pair_mask(int nrows, int ncols, int list_len, const long long* col_ids, const long long* row_ids0,
+                           const long long* row_lists, uint32_t* mask, uint32_t* mask_t, uint8_t* ws,
+                           cudaStream_t st) {
+  const PairMaskWs w = pair_mask_ws(ncols);
+  long long* keys = reinterpret_cast<long long*>(ws + w.keys_off);
+  int* heads = reinterpret_cast<int*>(ws + w.heads_off);
+  int* next = reinterpret_cast<int*>(ws + w.next_off);
+  const int words = mask_words_for(ncols), words_t = mask_words_for(nrows);
+  const int rows_pad = cdiv(nrows, BM) * BM, cols_pad = cdiv(ncols, BM) * BM;
+  {
+    const size_t total = static_cast<size_t>(rows_pad) * words;
+    mask_init_kernel<<<cdiv(total, 256), 256, 0, st>>>(mask, rows_pad, words, nrows, ncols);
+    XB_LAUNCHED();
+  }
+  if (mask_t != nullptr) {
+    const size_t total = static_cast<size_t>(cols_pad) * words_t;
+    mask_init_kernel<<<cdiv(total, 256), 256, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
+    XB_LAUNCHED();
+  }
+  const bool any_ids = (row_ids0 != nullptr) || (row_lists != nullptr && list_len > 0);
+  if (!any_ids || ncols == 0 || nrows == 0) return XB_OK;
+  hash_clear_kernel<<<cdiv(w.tsize, 256), 256, 0, st>>>(keys, heads, w.tsize);
+  XB_LAUNCHED();
+  hash_insert_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(col_ids, ncols, keys, heads, next, w.tsize - 1);
+  XB_LAUNCHED();
+  const int ll = (row_lists != nullptr) ? list_len : 0;
+  const long long threads = static_cast<long long>(nrows) * (ll + 1);
+  hash_mark_kernel<<<cdiv(threads, 256), 256, 0, st>>>(nrows, ll, row_ids0, row_lists, keys, heads, next, w.tsize - 1,
+                                                       mask, words, mask_t, words_t);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss workspace
+// ------------------------------------------------------------------------------------------------
+constexpr int MINE_CAP = 256;    // candidate buffer per row for the mining sweep
+constexpr int MINE_KMAX = 64;    // largest supported num_negatives
+constexpr int MINE_OVERFETCH = 32;  // extra candidates re-scored exactly before the final selection (<= 96 total)
+
+struct LossWs {
+  int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
+  bool mining;
+  SweepPlan fwd, gq, gi;   // forward / mining sweep, dQ sweep, dI sweep
+  size_t qprep, iprep, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
+      ueff, qg, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, total;
+};
+
+static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
+  w->kp = cdiv(d->dim, KBLK) * KBLK;
+  w->parts = d->compute == XB_COMPUTE_SPLIT ? 2 : 1;
+  const int B = d->batch, N = d->num_items;
+  w->B_pad = cdiv(B, BM) * BM;
+  w->N_pad = cdiv(N, BM) * BM;
+  w->words = mask_words_for(N);
+  w->words_t = mask_words_for(B);
+  w->K = d->num_negatives;
+  w->mining = d->num_negatives > 0 && d->num_negatives < N;
+  w->Kf = w->K + MINE_OVERFETCH;
+  const int lm = sweep_lm_from_mask(d->loss_mask);
+  const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
+  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, 2);
+  w->gq = plan_sweep(B, N, w->kp, w->parts, true, 2);
+  w->gi = plan_sweep(N, B, w->kp, w->parts, true, gq_floats);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + (bytes > 0 ? bytes : 1), 256);
+    return o;
+  };
+  const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
+  w->qprep = take(rowb * B);
+  w->iprep = take(rowb * N);
+  w->qn2 = take(sizeof(float) * B);
+  w->in2 = take(sizeof(float) * N);
+  w->qfwd = take(sizeof(float4) * B);
+  w->qmine = take(sizeof(float4) * B);
+  w->rowinfo = take(sizeof(float4) * B);
+  w->diag = take(sizeof(float) * B);
+  w->ipar = take(sizeof(float2) * N);
+  w->mask = take(sizeof(uint32_t) * w->B_pad * static_cast<size_t>(w->words));
+  w->mask_t = take(sizeof(uint32_t) * w->N_pad * static_cast<size_t>(w->words_t));
+  w->pm_ws = take(pair_mask_ws(N).total);
+  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
+  w->rowstat = take(sizeof(float4) * B);
+  w->rowloss = take(sizeof(float) * 7 * B);
+  w->ueff = take(sizeof(float) * 8);
+  w->qg = take(sizeof(float) * 12 * B);
+  const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
+  w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
+  w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * w->B_pad);
+  w->acci = take(sizeof(float) * static_cast<size_t>(ni) * w->N_pad * w->kp);
+  w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * w->N_pad);
+  w->gdiag = take(sizeof(float) * B);
+  if (w->mining) {
+    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad * MINE_CAP);
+    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
+    w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * w->Kf);
+    w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
+    w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
+  } else {
+    w->cand = w->cand_cnt = w->sel = w->selcol = w->selL2 = off;
+  }
+  w->total = off;
+  return w->fwd.ok && w->gq.ok && w->gi.ok;
+}
+
+static int check_loss_desc(const xb_loss_desc* d) {
+  if (d == nullptr) return fail(XB_ERR_INVALID_ARG, "desc is null");
+  if (d->batch <= 0 || d->num_items < d->batch)
+    return fail(XB_ERR_INVALID_ARG, "need 0 < batch <= num_items (batch=%d, num_items=%d)", d->batch, d->num_items);
+  if (d->dim <= 0 || d->num_pos < 0) return fail(XB_ERR_INVALID_ARG, "bad dim / num_pos");
+  if (d->in_dtype != XB_DTYPE_F32 && d->in_dtype != XB_DTYPE_BF16) return fail(XB_ERR_INVALID_ARG, "bad in_dtype");
+  if (d->compute != XB_COMPUTE_BF16 && d->compute != XB_COMPUTE_SPLIT) return fail(XB_ERR_INVALID_ARG, "bad compute");
+  if ((d->loss_mask & ~0x7fu) != 0 || d->loss_mask == 0) return fail(XB_ERR_INVALID_ARG, "bad loss_mask");
+  const int kp = cdiv(d->dim, KBLK) * KBLK;
+  if (kp > 256) return fail(XB_ERR_UNSUPPORTED, "dim %d > 256 is not supported", d->dim);
+  if (d->num_negatives > MINE_KMAX && d->num_negatives < d->num_items)
+    return fail(XB_ERR_UNSUPPORTED, "num_negatives %d > %d is not supported", d->num_negatives, MINE_KMAX);
+  LossWs w;
+  if (!loss_ws_layout(d, &w))
+    return fail(XB_ERR_UNSUPPORTED, "dim %d with compute=%d does not fit shared memory for this loss set", d->dim,
+                d->compute);
+  return XB_OK;
+}
+
+template <typename T>
+static int prep_operand(const void* x, int n, int d, int kp, int parts, void* out, float* norm2, cudaStream_t st) {
+  prep_operand_kernel<T><<<cdiv(static_cast<long long>(n) * 32, 256), 256, 0, st>>>(
+      static_cast<const T*>(x), n, d, kp, parts, static_cast<__nv_bfloat16*>(out), norm2);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+static SweepParams base_params(int nR, int nC, int kp, int parts, const SweepPlan& pl) {
+  SweepParams p{};
+  p.nR = nR;
+  p.nC = nC;
+  p.nR_pad = cdiv(nR, BM) * BM;
+  p.kp = kp;
+  p.parts = parts;
+  p.nstages = pl.nstages;
+  p.tiles_per_cta = pl.tiles_per_cta;
+  p.n_ctiles = pl.n_ctiles;
+  return p;
+}
+
+template <typename T>
+static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const float* d_losses, T* dq, T* di,
+                               uint8_t* ws, cudaStream_t st) {
+  int rc;
+  const int B = desc->batch, N = desc->num_items, d = desc->dim;
+  const int lm = sweep_lm_from_mask(desc->loss_mask);
+  float* ueff = reinterpret_cast<float*>(ws + w.ueff);
+  mask_upstream_kernel<<<1, 32, 0, st>>>(d_losses, desc->loss_mask, ueff);
+  XB_LAUNCHED();
+  __nv_bfloat16* qprep = reinterpret_cast<__nv_bfloat16*>(ws + w.qprep);
+  __nv_bfloat16* iprep = reinterpret_cast<__nv_bfloat16*>(ws + w.iprep);
+  float4* qfwd = reinterpret_cast<float4*>(ws + w.qfwd);
+  float4* rowinfo = reinterpret_cast<float4*>(ws + w.rowinfo);
+  float4* rowstat = reinterpret_cast<float4*>(ws + w.rowstat);
+  float* accq = reinterpret_cast<float*>(ws + w.accq);
+  float* rsq = reinterpret_cast<float*>(ws + w.rsq);
+  float* acci = reinterpret_cast<float*>(ws + w.acci);
+  float* rsi = reinterpret_cast<float*>(ws + w.rsi);
+  float* gdiag = reinterpret_cast<float*>(ws + w.gdiag);
+  int nq = 1, ni = 1;
+  if (lm == 0 || w.mining) {
+    XB_CUDA(cudaMemsetAsync(accq, 0, sizeof(float) * static_cast<size_t>(w.B_pad) * w.kp, st));
+    XB_CUDA(cudaMemsetAsync(rsq, 0, sizeof(float) * 2 * static_cast<size_t>(w.B_pad), st));
+    XB_CUDA(cudaMemsetAsync(acci, 0, sizeof(float) * static_cast<size_t>(w.N_pad) * w.kp, st));
+    XB_CUDA(cudaMemsetAsync(rsi, 0, sizeof(float) * 2 * static_cast<size_t>(w.N_pad), st));
+    if (lm != 0) {
+      mined_backward_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
+          B, w.K, w.kp, w.parts, reinterpret_cast<int*>(ws + w.selcol), reinterpret_cast<float*>(ws + w.selL2), qprep,
+          iprep, ueff, desc->sigma, qfwd, rowinfo, rowstat, accq, rsq, acci, rsi);
+      XB_LAUNCHED();
+    }
+  } else {
+    float* qg = reinterpret_cast<float*>(ws + w.qg);
+    grad_params_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, lm, ueff, desc->sigma, qfwd, rowinfo, rowstat, qg);
+    XB_LAUNCHED();
+    CUtensorMap tmQ, tmI;
+    if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
+    if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
+    {  // dQ sweep: rows = queries, columns = items
+      SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
+      p.rpar = qg;
+      p.cpar = reinterpret_cast<float*>(ws + w.ipar);
+      p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
+      p.mask_words = w.words;
+      p.out_acc = accq;
+      p.out_stats = rsq;
+      XB_CUDA(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
+                                     w.gq.smem, st));
+      ++g_launches;
+      nq = w.gq.nchunks;
+    }
+    {  // dI sweep: rows = items, columns = queries (transposed mask)
+      SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
+      p.rpar = reinterpret_cast<float*>(ws + w.ipar);
+      p.cpar = qg;
+      p.mask = reinterpret_cast<uint32_t*>(ws + w.mask_t);
+      p.mask_words = w.words_t;
+      p.out_acc = acci;
+      p.out_stats = rsi;
+      XB_CUDA(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
+                                     w.gi.smem, st));
+      ++g_launches;
+      ni = w.gi.nchunks;
+    }
+  }
+  grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+      B, d, w.kp, w.parts, w.B_pad, nq, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
+      dq, gdiag);
+  XB_LAUNCHED();
+  grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(N) * 32, 256), 256, 0, st>>>(
+      N, B, d, w.kp, w.parts, w.N_pad, ni, acci, rsi, iprep, qprep, gdiag, di);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* xb_last_error_string(void) { return g_last_error.c_str(); }
+const char* xb_version(void) { return "xfmr_b200 0.1 (sm_100a)"; }
+int64_t xb_launch_count(int32_t reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+int32_t xb_mask_words(int32_t num_items) { return mask_words_for(num_items); }
+
+// ------------------------------------------------------------------------------------------------ losses
+size_t xb_loss_workspace_bytes(const xb_loss_desc* desc) {
+  if (check_loss_desc(desc) != XB_OK) return 0;
+  LossWs w;
+  loss_ws_layout(desc, &w);
+  return w.total;
+}
+
+int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void* item_embed, const float* target,
+                    const int64_t* item_idx, const int64_t* pos_idx, const float* log_q, float* losses_out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_loss_desc(desc);
+  if (rc != XB_OK) return rc;
+  if (!user_embed || !item_embed || !target || !item_idx || !losses_out || !workspace)
+    return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (desc->num_pos > 0 && !pos_idx) return fail(XB_ERR_INVALID_ARG, "pos_idx is null but num_pos > 0");
+  if (desc->has_log_q && !log_q) return fail(XB_ERR_INVALID_ARG, "has_log_q set but log_q is null");
+  LossWs w;
+  loss_ws_layout(desc, &w);
+  if (workspace_bytes < w.total) return fail(XB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int B = desc->batch, N = desc->num_items, d = desc->dim;
+  const float* lq = desc->has_log_q ? log_q : nullptr;
+
+  // 1. operands -> bf16 (hi [, lo]) + norms
+  if (desc->in_dtype == XB_DTYPE_F32) {
+    if ((rc = prep_operand<float>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), st))) return rc;
+    if ((rc = prep_operand<float>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), st))) return rc;
+  } else {
+    if ((rc = prep_operand<__nv_bfloat16>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), st))) return rc;
+  }
+  // 2. per-row / per-column parameters of the logit map
+  query_params_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+      B, w.kp, w.parts, reinterpret_cast<__nv_bfloat16*>(ws + w.qprep), reinterpret_cast<__nv_bfloat16*>(ws + w.iprep),
+      reinterpret_cast<float*>(ws + w.qn2), target, lq, desc->sigma, desc->margin,
+      reinterpret_cast<float4*>(ws + w.qfwd), reinterpret_cast<float4*>(ws + w.qmine),
+      reinterpret_cast<float4*>(ws + w.rowinfo), reinterpret_cast<float*>(ws + w.diag));
+  XB_LAUNCHED();
+  item_params_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, reinterpret_cast<float*>(ws + w.in2), lq,
+                                                   reinterpret_cast<float2*>(ws + w.ipar));
+  XB_LAUNCHED();
+
+  const int lm = sweep_lm_from_mask(desc->loss_mask);
+  float4* rowstat = reinterpret_cast<float4*>(ws + w.rowstat);
+  float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
+  if (lm != 0) {
+    // 3. false-negative mask (losses.py:92-110) and its transpose
+    rc = build_pair_mask(B, N, desc->num_pos, reinterpret_cast<const long long*>(item_idx),
+                         reinterpret_cast<const long long*>(item_idx), reinterpret_cast<const long long*>(pos_idx),
+                         reinterpret_cast<uint32_t*>(ws + w.mask), reinterpret_cast<uint32_t*>(ws + w.mask_t),
+                         ws + w.pm_ws, st);
+    if (rc != XB_OK) return rc;
+    // 4. the sweep
+    CUtensorMap tmQ, tmI;
+    if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
+    if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
+    SweepParams p = base_params(B, N, w.kp, w.parts, w.fwd);
+    p.cpar = reinterpret_cast<float*>(ws + w.ipar);
+    p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
+    p.mask_words = w.words;
+    const dim3 grid(w.fwd.nchunks, w.fwd.n_rblocks);
+    if (!w.mining) {
+      p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
+      p.out_stats = reinterpret_cast<float*>(ws + w.part);
+      XB_CUDA(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
+      ++g_launches;
+      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks, p.out_stats, desc->sigma,
+                                                     reinterpret_cast<float4*>(ws + w.rowinfo),
+                                                     reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
+      XB_LAUNCHED();
+    } else {
+      // semi-hard mining (losses.py:134-162): streaming selection of the K best columns per row, then
+      // the sparse loss on those columns
+      p.rpar = reinterpret_cast<float*>(ws + w.qmine);
+      p.cand = reinterpret_cast<unsigned long long*>(ws + w.cand);
+      p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
+      p.cap = MINE_CAP;
+      p.keep = w.Kf;
+      p.topk_mining = 1;
+      XB_CUDA(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
+      ++g_launches;
+      cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
+          B, p.nR_pad, w.fwd.nchunks, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
+          reinterpret_cast<unsigned long long*>(ws + w.sel));
+      XB_LAUNCHED();
+      // exact re-score from the original inputs when they carry more precision than the operands
+      const bool use_orig = (desc->in_dtype == XB_DTYPE_F32 && desc->compute == XB_COMPUTE_SPLIT);
+      mined_forward_kernel<float><<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
+          B, w.K, w.Kf, d, w.kp, w.parts, reinterpret_cast<unsigned long long*>(ws + w.sel),
+          use_orig ? static_cast<const float*>(user_embed) : nullptr,
+          use_orig ? static_cast<const float*>(item_embed) : nullptr,
+          reinterpret_cast<__nv_bfloat16*>(ws + w.qprep), reinterpret_cast<__nv_bfloat16*>(ws + w.iprep),
+          reinterpret_cast<float4*>(ws + w.qfwd), reinterpret_cast<float2*>(ws + w.ipar),
+          reinterpret_cast<float4*>(ws + w.rowinfo), reinterpret_cast<float*>(ws + w.diag), desc->sigma,
+          reinterpret_cast<int*>(ws + w.selcol), reinterpret_cast<float*>(ws + w.selL2), rowstat, rowloss);
+      XB_LAUNCHED();
+    }
+  } else {
+    // AlignmentLoss only: diagonal terms, no sweep.  An empty partial set gives cnt = 0.
+    loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, w.B_pad, 0, nullptr, desc->sigma,
+                                                   reinterpret_cast<float4*>(ws + w.rowinfo),
+                                                   reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
+    XB_LAUNCHED();
+  }
+  loss_reduce_kernel<<<XB_NUM_LOSSES, 256, 0, st>>>(B, rowloss, desc->loss_mask, losses_out);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_loss_backward(const xb_loss_desc* desc, const float* d_losses, void* d_user, void* d_item, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  int rc = check_loss_desc(desc);
+  if (rc != XB_OK) return rc;
+  if (!d_losses || !d_user || !d_item || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  LossWs w;
+  loss_ws_layout(desc, &w);
+  if (workspace_bytes < w.total) return fail(XB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  if (desc->in_dtype == XB_DTYPE_F32)
+    return loss_backward_typed<float>(desc, w, d_losses, static_cast<float*>(d_user), static_cast<float*>(d_item), ws, st);
+  return loss_backward_typed<__nv_bfloat16>(desc, w, d_losses, static_cast<__nv_bfloat16*>(d_user),
+                                            static_cast<__nv_bfloat16*>(d_item), ws, st);
+}
+
+// ------------------------------------------------------------------------------------------------ pair mask
+size_t xb_pair_mask_workspace_bytes(int32_t num_cols) {
+  if (num_cols < 0) return 0;
+  return pair_mask_ws(num_cols).total;
+}
+
+int xb_build_pair_mask(int32_t num_rows, int32_t num_cols, int32_t list_len, const int64_t* col_ids,
+                       const int64_t* row_ids0, const int64_t* row_id_lists, uint32_t* mask, uint32_t* mask_t,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (num_rows <= 0 || num_cols <= 0 || list_len < 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (!col_ids || !mask || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (list_len > 0 && !row_id_lists) return fail(XB_ERR_INVALID_ARG, "row_id_lists is null but list_len > 0");
+  if (workspace_bytes < pair_mask_ws(num_cols).total) return fail(XB_ERR_WORKSPACE, "workspace too small");
+  return build_pair_mask(num_rows, num_cols, list_len, reinterpret_cast<const long long*>(col_ids),
+                         reinterpret_cast<const long long*>(row_ids0), reinterpret_cast<const long long*>(row_id_lists),
+                         mask, mask_t, static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ top-k
+namespace {
+struct TopkWs {
+  int kp, parts, Q_pad, cap, kfetch;
+  SweepPlan plan;
+  size_t qprep, iprep, cand, cand_cnt, ent, scores, ids, total;
+  bool items_inplace;  // the caller's bf16 catalog already has the prepared layout
+};
+int topk_cap_for(int kfetch) {
+  int cap = 64;
+  while (cap < 2 * kfetch + 32) cap <<= 1;
+  return cap;
+}
+bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
+  w->kp = cdiv(d->dim, KBLK) * KBLK;
+  w->parts = d->compute == XB_COMPUTE_SPLIT ? 2 : 1;
+  w->Q_pad = cdiv(d->num_queries, BM) * BM;
+  // over-fetch: candidates are ranked by tensor-core scores whose rounding differs from the final
+  // (re-)score, so a margin of extra candidates protects the k-th boundary.
+  w->kfetch = d->k + (d->k < 32 ? 16 : 32);
+  if (w->kfetch > d->num_items) w->kfetch = d->num_items > 0 ? d->num_items : 1;
+  w->cap = topk_cap_for(w->kfetch);
+  w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, 2);
+  w->items_inplace = (d->in_dtype == XB_DTYPE_BF16 && w->parts == 1 && d->dim == w->kp);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + (bytes > 0 ? bytes : 1), 256);
+    return o;
+  };
+  const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
+  w->qprep = take(rowb * d->num_queries);
+  w->iprep = take(w->items_inplace ? 0 : rowb * static_cast<size_t>(d->num_items));
+  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * w->Q_pad * w->cap);
+  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * w->Q_pad);
+  w->ent = take(sizeof(unsigned long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
+  w->scores = take(sizeof(float) * static_cast<size_t>(d->num_queries) * w->kfetch);
+  w->ids = take(sizeof(long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
+  w->total = off;
+  return w->plan.ok && w->cap <= 1024;
+}
+int check_topk_desc(const xb_topk_desc* d) {
+  if (d == nullptr) return fail(XB_ERR_INVALID_ARG, "desc is null");
+  if (d->num_queries <= 0 || d->num_items <= 0 || d->dim <= 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (d->k <= 0 || d->k > 256) return fail(XB_ERR_UNSUPPORTED, "k must be in 1..256 (k=%d)", d->k);
+  if (d->in_dtype != XB_DTYPE_F32 && d->in_dtype != XB_DTYPE_BF16) return fail(XB_ERR_INVALID_ARG, "bad in_dtype");
+  if (d->compute != XB_COMPUTE_BF16 && d->compute != XB_COMPUTE_SPLIT) return fail(XB_ERR_INVALID_ARG, "bad compute");
+  if (cdiv(d->dim, KBLK) * KBLK > 256) return fail(XB_ERR_UNSUPPORTED, "dim %d > 256 is not supported", d->dim);
+  TopkWs w;
+  if (!topk_ws_layout(d, &w)) return fail(XB_ERR_UNSUPPORTED, "dim/compute combination does not fit shared memory");
+  return XB_OK;
+}
+}  // namespace
+
+size_t xb_topk_workspace_bytes(const xb_topk_desc* desc) {
+  if (check_topk_desc(desc) != XB_OK) return 0;
+  TopkWs w;
+  topk_ws_layout(desc, &w);
+  return w.total;
+}
+
+int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* items, const int64_t* item_ids,
+                   const uint32_t* excl_mask, float* scores_out, int64_t* ids_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  int rc = check_topk_desc(desc);
+  if (rc != XB_OK) return rc;
+  if (!queries || !items || !scores_out || !ids_out || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (desc->has_exclusions && !excl_mask) return fail(XB_ERR_INVALID_ARG, "has_exclusions set but excl_mask is null");
+  TopkWs w;
+  topk_ws_layout(desc, &w);
+  if (workspace_bytes < w.total) return fail(XB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int Q = desc->num_queries, N = desc->num_items, d = desc->dim, k = desc->k;
+
+  const void* iprep = items;
+  if (desc->in_dtype == XB_DTYPE_F32) {
+    if ((rc = prep_operand<float>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, st))) return rc;
+    iprep = ws + w.iprep;
+  } else {
+    if ((rc = prep_operand<__nv_bfloat16>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, st))) return rc;
+    if (!w.items_inplace) {
+      if ((rc = prep_operand<__nv_bfloat16>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, st))) return rc;
+      iprep = ws + w.iprep;
+    }
+  }
+  CUtensorMap tmQ, tmI;
+  if ((rc = make_operand_map(&tmQ, ws + w.qprep, Q, static_cast<long long>(w.parts) * w.kp))) return rc;
+  if ((rc = make_operand_map(&tmI, iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
+  SweepParams p = base_params(Q, N, w.kp, w.parts, w.plan);
+  p.mask = desc->has_exclusions ? excl_mask : nullptr;
+  p.mask_words = mask_words_for(N);
+  p.cand = reinterpret_cast<unsigned long long*>(ws + w.cand);
+  p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
+  p.cap = w.cap;
+  p.keep = w.kfetch;
+  p.topk_mining = 0;
+  XB_CUDA(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
+  ++g_launches;
+  unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
+  cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(Q, p.nR_pad, w.plan.nchunks, w.cap,
+                                                                                 w.kfetch, p.cand, p.cand_cnt, ent);
+  XB_LAUNCHED();
+  float* stmp = reinterpret_cast<float*>(ws + w.scores);
+  long long* itmp = reinterpret_cast<long long*>(ws + w.ids);
+  const long long nent = static_cast<long long>(Q) * w.kfetch;
+  if (desc->compute == XB_COMPUTE_SPLIT && desc->in_dtype == XB_DTYPE_F32) {
+    topk_rescore_kernel<float><<<cdiv(nent, 128), 128, 0, st>>>(Q, w.kfetch, d, ent, static_cast<const float*>(queries),
+                                                                static_cast<const float*>(items),
+                                                                reinterpret_cast<const long long*>(item_ids),
+                                                                desc->id_base, stmp, itmp);
+  } else {
+    topk_emit_kernel<<<cdiv(nent * 32, 256), 256, 0, st>>>(Q, w.kfetch, w.kp, w.parts, ent,
+                                                           reinterpret_cast<__nv_bfloat16*>(ws + w.qprep),
+                                                           static_cast<const __nv_bfloat16*>(iprep),
+                                                           reinterpret_cast<const long long*>(item_ids), desc->id_base,
+                                                           stmp, itmp);
+  }
+  XB_LAUNCHED();
+  fill_topk_empty_kernel<<<cdiv(static_cast<long long>(Q) * k, 256), 256, 0, st>>>(static_cast<size_t>(Q) * k, scores_out,
+                                                                                  reinterpret_cast<long long*>(ids_out));
+  XB_LAUNCHED();
+  pairs_select_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(Q, w.kfetch, k, stmp, itmp, scores_out,
+                                                                                reinterpret_cast<long long*>(ids_out));
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_topk_merge(int32_t num_queries, int32_t num_lists, int32_t list_len, int32_t k, const float* in_scores,
+                  const int64_t* in_ids, float* scores_out, int64_t* ids_out, void* stream) {
+  if (num_queries <= 0 || num_lists <= 0 || list_len <= 0 || k <= 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (!in_scores || !in_ids || !scores_out || !ids_out) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fill_topk_empty_kernel<<<cdiv(static_cast<long long>(num_queries) * k, 256), 256, 0, st>>>(
+      static_cast<size_t>(num_queries) * k, scores_out, reinterpret_cast<long long*>(ids_out));
+  XB_LAUNCHED();
+  pairs_select_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
+      num_queries, num_lists * list_len, k, in_scores, reinterpret_cast<const long long*>(in_ids), scores_out,
+      reinterpret_cast<long long*>(ids_out));
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hash gather
+int xb_hash_indices(const int64_t* ids, int64_t n, int32_t num_hashes, uint32_t seed0, int32_t log2_rows,
+                    int32_t* idx_out, void* stream) {
+  if (n < 0 || num_hashes <= 0 || log2_rows < 0 || log2_rows > 31) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (n == 0) return XB_OK;
+  if (!ids || !idx_out) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  const uint32_t row_mask = (log2_rows == 32) ? 0xffffffffu : ((1u << log2_rows) - 1u);
+  hash_indices_kernel<<<cdiv(n * num_hashes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), n, num_hashes, seed0, row_mask, idx_out);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_hash_gather(const int64_t* ids, int64_t n, int32_t num_hashes, uint32_t seed0, const void* table,
+                   int32_t log2_rows, int32_t dim, void* out, int32_t* idx_out, void* stream) {
+  if (n < 0 || num_hashes <= 0 || log2_rows < 0 || log2_rows > 31 || dim <= 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (dim % 8 != 0) return fail(XB_ERR_UNSUPPORTED, "dim must be a multiple of 8 (128-bit rows), got %d", dim);
+  if (n == 0) return XB_OK;
+  if (!ids || !table || !out) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  const uint32_t row_mask = (1u << log2_rows) - 1u;
+  const int vec_per_row = dim / 8;
+  int lpr = 1;
+  while (lpr < vec_per_row && lpr < 32) lpr <<= 1;
+  hash_gather_kernel<<<cdiv(n * lpr, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), n, num_hashes, seed0, static_cast<const uint4*>(table), row_mask, dim,
+      static_cast<uint4*>(out), idx_out, lpr);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_hash_scatter_grad(const int64_t* ids, int64_t n, int32_t num_hashes, uint32_t seed0, const void* d_out,
+                         int32_t log2_rows, int32_t dim, float* d_table, void* stream) {
+  if (n < 0 || num_hashes <= 0 || log2_rows < 0 || log2_rows > 31 || dim <= 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (n == 0) return XB_OK;
+  if (!ids || !d_out || !d_table) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  const uint32_t row_mask = (1u << log2_rows) - 1u;
+  hash_scatter_grad_kernel<<<cdiv(n * dim, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), n, num_hashes, seed0, static_cast<const __nv_bfloat16*>(d_out), row_mask,
+      dim, d_table);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ debug
+namespace {
+struct DebugWs {
+  int kp, parts;
+  SweepPlan plan;
+  size_t rprep, cprep, rs, total;
+};
+bool debug_ws_layout(int nR, int nC, int dim, int compute, DebugWs* w) {
+  w->kp = cdiv(dim, KBLK) * KBLK;
+  w->parts = compute == XB_COMPUTE_SPLIT ? 2 : 1;
+  w->plan = plan_sweep(nR, nC, w->kp, w->parts, true, 2);
+  // one chunk so that acc_out is the complete product
+  w->plan.nchunks = 1;
+  w->plan.tiles_per_cta = w->plan.n_ctiles;
+  size_t off = 0;
+  const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
+  w->rprep = off; off = align_up(off + rowb * nR, 256);
+  w->cprep = off; off = align_up(off + rowb * nC, 256);
+  w->rs = off; off = align_up(off + sizeof(float) * 2 * cdiv(nR, BM) * BM, 256);
+  w->total = off;
+  return w->plan.ok;
+}
+}  // namespace
+
+size_t xb_debug_workspace_bytes(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t compute) {
+  if (num_rows <= 0 || num_cols <= 0 || dim <= 0 || dim > 256) return 0;
+  DebugWs w;
+  if (!debug_ws_layout(num_rows, num_cols, dim, compute, &w)) return 0;
+  return w.total;
+}
+
+int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_dtype, int32_t compute,
+                    const void* rows, const void* cols, float* s_out, float* acc_out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (num_rows <= 0 || num_cols <= 0 || dim <= 0 || dim > 256) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (!rows || !cols || !s_out || !acc_out || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  DebugWs w;
+  if (!debug_ws_layout(num_rows, num_cols, dim, compute, &w)) return fail(XB_ERR_UNSUPPORTED, "does not fit shared memory");
+  if (workspace_bytes < w.total) return fail(XB_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int rc;
+  if (in_dtype == XB_DTYPE_F32) {
+    if ((rc = prep_operand<float>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, st))) return rc;
+  } else {
+    if ((rc = prep_operand<__nv_bfloat16>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, st))) return rc;
+  }
+  CUtensorMap tmR, tmC;
+  if ((rc = make_operand_map(&tmR, ws + w.rprep, num_rows, static_cast<long long>(w.parts) * w.kp))) return rc;
+  if ((rc = make_operand_map(&tmC, ws + w.cprep, num_cols, static_cast<long long>(w.parts) * w.kp))) return rc;
+  SweepParams p = base_params(num_rows, num_cols, w.kp, w.parts, w.plan);
+  p.dbg_s = s_out;
+  p.out_acc = acc_out;
+  p.out_stats = reinterpret_cast<float*>(ws + w.rs);
+  XB_CUDA(launch_sweep_debug(tmR, tmC, p, dim3(1, w.plan.n_rblocks), w.plan.smem, st));
+  ++g_launches;
+  return XB_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

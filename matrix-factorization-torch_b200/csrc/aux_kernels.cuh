@@ -1,0 +1,735 @@
+// Plain (non tensor-core) kernels around the sweep: operand preparation, the false-negative pair mask,
+// per-row finalisation of the loss statistics, gradient parameter / diagonal handling, the sparse path
+// of semi-hard mining, top-k finalisation and the hashed-embedding gather.  All HBM-bound or tiny.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "sweep.cuh"
+
+namespace xb {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr long long EMPTY_KEY = static_cast<long long>(0x8000000000000000ull);  // INT64_MIN never an id
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+// value the tensor cores see for element k of a prepared row: hi (+ lo)
+__device__ __forceinline__ float prepped_val(const __nv_bfloat16* row, int kp, int parts, int k) {
+  float v = __bfloat162float(row[k]);
+  if (parts == 2) v += __bfloat162float(row[kp + k]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operand preparation: x [n, d] (fp32 or bf16) -> bf16 [n, parts * kp] (zero padded to kp, optional
+// hi/lo split) and the squared norm of the prepared values.  One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void prep_operand_kernel(const T* __restrict__ x, int n, int d, int kp, int parts,
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const T* xr = x + static_cast<size_t>(row) * d;
+  __nv_bfloat16* o = out + static_cast<size_t>(row) * parts * kp;
+  float acc = 0.f;
+  for (int k = lane; k < kp; k += 32) {
+    const float v = k < d ? static_cast<float>(xr[k]) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    float e = __bfloat162float(hi);
+    o[k] = hi;
+    if (parts == 2) {
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - e);
+      o[kp + k] = lo;
+      e = v;  // split operands represent v to ~2^-17: take the norm of v itself
+    }
+    acc = fmaf(e, e, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && norm2 != nullptr) norm2[row] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-query and per-item parameters of the logit map (see sweep.cuh).  One warp per row.
+//   rowinfo[i] = {sign, |target|, target, L2_ii}       diag[i] = S_ii = -|q_i - v_i|^2 / 2
+//   qfwd[i]    = {a2, r2, xoff, sm2}                   qmine[i] = {a2, r2, -L2_ii, 0}
+// ------------------------------------------------------------------------------------------------
+__global__ void query_params_kernel(int B, int kp, int parts, const __nv_bfloat16* __restrict__ qp,
+                                    const __nv_bfloat16* __restrict__ ip, const float* __restrict__ qn2,
+                                    const float* __restrict__ target, const float* __restrict__ log_q,
+                                    float sigma, float margin, float4* __restrict__ qfwd,
+                                    float4* __restrict__ qmine, float4* __restrict__ rowinfo,
+                                    float* __restrict__ diag) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
+  const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
+  float acc = 0.f;
+  for (int k = lane; k < kp; k += 32) {
+    const float dlt = prepped_val(q, kp, parts, k) - prepped_val(v, kp, parts, k);
+    acc = fmaf(dlt, dlt, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float t = target[row];
+    const float s = t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f);
+    const float w = fabsf(t);
+    const float a2 = sigma * s * LOG2E;
+    const float dg = -0.5f * acc;
+    const float lq2 = log_q != nullptr ? log_q[row] * LOG2E : 0.f;
+    const float l2ii = a2 * dg - lq2;
+    const float m2 = margin * LOG2E;
+    const float r2 = -0.5f * a2 * qn2[row];
+    qfwd[row] = make_float4(a2, r2, m2 - l2ii, s * m2);
+    qmine[row] = make_float4(a2, r2, -l2ii, 0.f);
+    rowinfo[row] = make_float4(s, w, t, l2ii);
+    diag[row] = dg;
+  }
+}
+
+__global__ void item_params_kernel(int N, const float* __restrict__ in2, const float* __restrict__ log_q,
+                                   float2* __restrict__ ipar) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  ipar[j] = make_float2(-0.5f * in2[j], log_q != nullptr ? log_q[j] * LOG2E : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pair mask (bit set = excluded).  Hash table: open addressing on the 64-bit id, every slot heads a
+// linked list of the columns that carry that id.
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_init_kernel(uint32_t* __restrict__ mask, int rows_pad, int words, int rows_valid,
+                                 int cols_valid) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(rows_pad) * words;
+  if (i >= total) return;
+  const int r = static_cast<int>(i / words);
+  const int w = static_cast<int>(i % words);
+  uint32_t v;
+  if (r >= rows_valid) {
+    v = 0xffffffffu;
+  } else {
+    const int rem = cols_valid - w * 32;
+    v = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+  }
+  mask[i] = v;
+}
+
+__device__ __forceinline__ uint32_t hash64(long long id) {
+  unsigned long long x = static_cast<unsigned long long>(id);
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return static_cast<uint32_t>(x);
+}
+
+__global__ void hash_clear_kernel(long long* __restrict__ keys, int* __restrict__ heads, int tsize) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tsize) return;
+  keys[i] = EMPTY_KEY;
+  heads[i] = -1;
+}
+
+__global__ void hash_insert_kernel(const long long* __restrict__ col_ids, int ncols, long long* keys,
+                                   int* heads, int* __restrict__ next, int tmask) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  const long long id = col_ids[j];
+  uint32_t slot = hash64(id) & tmask;
+  while (true) {
+    const long long prev = static_cast<long long>(
+        atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot), static_cast<unsigned long long>(EMPTY_KEY),
+                  static_cast<unsigned long long>(id)));
+    if (prev == EMPTY_KEY || prev == id) break;
+    slot = (slot + 1) & tmask;
+  }
+  next[j] = atomicExch(heads + slot, j);
+}
+
+// one thread per (row, list entry); entry index list_len stands for row_ids0[row]
+__global__ void hash_mark_kernel(int nrows, int list_len, const long long* __restrict__ row_ids0,
+                                 const long long* __restrict__ row_lists, const long long* __restrict__ keys,
+                                 const int* __restrict__ heads, const int* __restrict__ next, int tmask,
+                                 uint32_t* mask, int words, uint32_t* mask_t, int words_t) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per_row = list_len + 1;
+  if (gid >= static_cast<long long>(nrows) * per_row) return;
+  const int r = static_cast<int>(gid / per_row);
+  const int e = static_cast<int>(gid % per_row);
+  long long id;
+  if (e == list_len) {
+    if (row_ids0 == nullptr) return;
+    id = row_ids0[r];
+  } else {
+    id = row_lists[static_cast<size_t>(r) * list_len + e];
+  }
+  if (id == EMPTY_KEY) return;
+  uint32_t slot = hash64(id) & tmask;
+  while (true) {
+    const long long k = keys[slot];
+    if (k == EMPTY_KEY) return;
+    if (k == id) break;
+    slot = (slot + 1) & tmask;
+  }
+  for (int c = heads[slot]; c >= 0; c = next[c]) {
+    atomicOr(mask + static_cast<size_t>(r) * words + (c >> 5), 1u << (c & 31));
+    if (mask_t != nullptr) atomicOr(mask_t + static_cast<size_t>(c) * words_t + (r >> 5), 1u << (r & 31));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward finalisation.  Merges the per-chunk partial statistics of a row and evaluates the seven
+// per-row loss terms (natural-log units).  rowstat[i] = {cnt, lseM2, lseI2, 1/(cnt + 1e-10)}.
+// rowloss is [7][B].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float logaddexp2(float a, float b) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  if (hi == -INFINITY) return -INFINITY;
+  return hi + log2f(1.f + exp2f(lo - hi));
+}
+
+__device__ __forceinline__ void write_row_losses(int row, int B, float sigma, const float4 ri, float dg,
+                                                 float cnt, float csum2, float hsum2, float lsum2, float lseM2,
+                                                 float4* rowstat, float* rowloss) {
+  const float w = ri.y, t = ri.z, l2ii = ri.w;
+  const float inv = 1.f / (cnt + 1e-10f);
+  const float lseI2 = logaddexp2(lseM2, l2ii);
+  rowstat[row] = make_float4(cnt, lseM2, lseI2, inv);
+  const float align = -dg * t * sigma;
+  const float contr = w * (csum2 * LN2 * inv);
+  rowloss[0 * B + row] = align;
+  rowloss[1 * B + row] = contr;
+  rowloss[2 * B + row] = align + contr;
+  rowloss[3 * B + row] = w * (LN2 * (lseI2 - l2ii));
+  rowloss[4 * B + row] = w * (LN2 * (lseM2 - l2ii));
+  rowloss[5 * B + row] = w * (hsum2 * LN2 * inv);
+  rowloss[6 * B + row] = w * (lsum2 * LN2 * inv);
+}
+
+__global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __restrict__ part, float sigma,
+                                 const float4* __restrict__ rowinfo, const float* __restrict__ diag,
+                                 float4* __restrict__ rowstat, float* __restrict__ rowloss) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float4* p = reinterpret_cast<const float4*>(part + (static_cast<size_t>(c) * nR_pad + row) * 8);
+    const float4 a = p[0], b = p[1];
+    cnt += a.x; csum += a.y; hsum += a.z; lsum += a.w;
+    if (b.y > 0.f) {
+      if (b.x > mx) { se = se * exp2f(mx - b.x) + b.y; mx = b.x; }
+      else se += b.y * exp2f(b.x - mx);
+    }
+  }
+  const float lseM2 = se > 0.f ? mx + log2f(se) : -INFINITY;
+  write_row_losses(row, B, sigma, rowinfo[row], diag[row], cnt, csum, hsum, lsum, lseM2, rowstat, rowloss);
+}
+
+// deterministic sum of each of the 7 row-loss vectors: one block per loss
+__global__ void loss_reduce_kernel(int B, const float* __restrict__ rowloss, uint32_t loss_mask,
+                                   float* __restrict__ losses) {
+  __shared__ double sh[256];
+  const int l = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) acc += static_cast<double>(rowloss[static_cast<size_t>(l) * B + i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) losses[l] = ((loss_mask >> l) & 1u) ? static_cast<float>(sh[0]) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  Upstream gradients u[7] (output order) fold into per-loss coefficients
+//   uA = u0 + u2 (alignment), uC = u1 + u2, uI = u3, uM = u4, uH = u5, uL = u6.
+// Per query:  k_l = a * u_l * w (/ cnt for the mean losses), off_l as in sweep.cuh, where a = sigma*sign.
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_upstream_kernel(const float* __restrict__ u, uint32_t loss_mask, float* __restrict__ u_eff) {
+  const int l = threadIdx.x;
+  if (l < 8) u_eff[l] = (l < 7 && ((loss_mask >> l) & 1u)) ? u[l] : 0.f;
+}
+
+struct GradCoef {
+  float a2, offC, kC, offI, kI, offM, kM, offH, kH, offL, kL;
+};
+
+__device__ __forceinline__ GradCoef grad_coef(const float* __restrict__ u, float sigma, const float4 qf,
+                                              const float4 ri, const float4 rs) {
+  GradCoef g;
+  const float a = sigma * ri.x, w = ri.y;
+  const float uC = u[1] + u[2], uI = u[3], uM = u[4], uH = u[5], uL = u[6];
+  g.a2 = qf.x;
+  g.offC = qf.y + qf.w;
+  g.kC = a * uC * w * rs.w;
+  g.offH = qf.y + qf.z;
+  g.kH = a * uH * w * rs.w;
+  g.offL = g.offH;
+  g.kL = a * uL * w * rs.w;
+  const bool okM = rs.y > -INFINITY, okI = rs.z > -INFINITY;
+  g.offM = okM ? qf.y - rs.y : 0.f;
+  g.kM = okM ? a * uM * w : 0.f;
+  g.offI = okI ? qf.y - rs.z : 0.f;
+  g.kI = okI ? a * uI * w : 0.f;
+  return g;
+}
+
+__global__ void grad_params_kernel(int B, int lm, const float* __restrict__ u, float sigma,
+                                   const float4* __restrict__ qfwd, const float4* __restrict__ rowinfo,
+                                   const float4* __restrict__ rowstat, float* __restrict__ qg) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B) return;
+  const GradCoef g = grad_coef(u, sigma, qfwd[row], rowinfo[row], rowstat[row]);
+  if (lm_single(lm)) {
+    float off = 0.f, k = 0.f;
+    if (lm == LM_CONTR) { off = g.offC; k = g.kC; }
+    if (lm == LM_INFONCE) { off = g.offI; k = g.kI; }
+    if (lm == LM_MINE) { off = g.offM; k = g.kM; }
+    if (lm == LM_HINGE) { off = g.offH; k = g.kH; }
+    if (lm == LM_LOGI) { off = g.offL; k = g.kL; }
+    reinterpret_cast<float4*>(qg)[row] = make_float4(g.a2, off, k, 0.f);
+  } else {
+    float4* o = reinterpret_cast<float4*>(qg + static_cast<size_t>(row) * 12);
+    o[0] = make_float4(g.a2, g.offC, g.kC, g.offI);
+    o[1] = make_float4(g.kI, g.offM, g.kM, g.offH);
+    o[2] = make_float4(g.kH, g.offL, g.kL, 0.f);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_out(T* p, float v);
+template <>
+__device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// dQ_i = sum_j G_ij v_j + G_ii v_i - (RG_i + G_ii) q_i          (dS/dq = v - q)
+// G_ii = -target*sigma*uA - RGH_i + a*w*(uI*(p_ii - 1) - uM)
+// One warp per query row.  gdiag[i] = G_ii is kept for the item-side finalisation.
+template <typename T>
+__global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_pad, int nchunks,
+                                       const float* __restrict__ acc, const float* __restrict__ rs_part,
+                                       const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ ip,
+                                       const float* __restrict__ u, float sigma, uint32_t loss_mask,
+                                       const float4* __restrict__ rowinfo, const float4* __restrict__ rowstat,
+                                       T* __restrict__ dq, float* __restrict__ gdiag) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float rg = 0.f, rgh = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);
+    rg += r.x;
+    rgh += r.y;
+  }
+  const float4 ri = rowinfo[row], rst = rowstat[row];
+  const float a = sigma * ri.x, w = ri.y, t = ri.z, l2ii = ri.w;
+  const float uA = ((loss_mask >> 0) & 1u ? u[0] : 0.f) + ((loss_mask >> 2) & 1u ? u[2] : 0.f);
+  const float uI = (loss_mask >> 3) & 1u ? u[3] : 0.f;
+  const float uM = (loss_mask >> 4) & 1u ? u[4] : 0.f;
+  float gii = -t * sigma * uA - rgh;
+  if (uI != 0.f && rst.z > -INFINITY) gii += a * w * uI * (exp2f(l2ii - rst.z) - 1.f);
+  if (uM != 0.f) gii -= a * w * uM;
+  if (lane == 0) gdiag[row] = gii;
+  const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
+  const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
+  for (int k = lane; k < d; k += 32) {
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
+    const float qv = prepped_val(q, kp, parts, k), vv = prepped_val(v, kp, parts, k);
+    store_out<T>(dq + static_cast<size_t>(row) * d + k, s + gii * vv - (rg + gii) * qv);
+  }
+}
+
+// dV_j = sum_i G_ij q_i - CG_j v_j + [j < B] G_jj (q_j - v_j)     (dS/dv = q - v)
+template <typename T>
+__global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, int nR_pad, int nchunks,
+                                       const float* __restrict__ acc, const float* __restrict__ rs_part,
+                                       const __nv_bfloat16* __restrict__ ip, const __nv_bfloat16* __restrict__ qp,
+                                       const float* __restrict__ gdiag, T* __restrict__ di) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float cg = 0.f;
+  for (int c = 0; c < nchunks; ++c) cg += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
+  const float gjj = row < B ? gdiag[row] : 0.f;
+  const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
+  const __nv_bfloat16* q = qp + static_cast<size_t>(row < B ? row : 0) * parts * kp;
+  for (int k = lane; k < d; k += 32) {
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
+    const float vv = prepped_val(v, kp, parts, k);
+    const float qv = row < B ? prepped_val(q, kp, parts, k) : 0.f;
+    store_out<T>(di + static_cast<size_t>(row) * d + k, s - cg * vv + gjj * (qv - vv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate-list finalisation (top-k and mining): merge the per-chunk buffers of a row, sort by
+// (key desc, column asc) and emit the first k entries.  One warp per row; total entries <= 1024.
+// ------------------------------------------------------------------------------------------------
+__global__ void cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap, int k,
+                                     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt,
+                                     unsigned long long* __restrict__ out /*[nrows][k]*/) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  // Repeated fold: keep the running best (<= 512) in registers, fold in one chunk buffer (<= 512 used
+  // entries after its own compaction... a raw buffer may hold up to cap entries) at a time.
+  unsigned long long best[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) best[i] = 0ull;
+  // slots [0,16) of `best` hold the running top-512, slots [16,32) receive new entries
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t r = static_cast<size_t>(c) * nR_pad + row;
+    const int n = cand_cnt[r];
+    const unsigned long long* buf = cand + r * cap;
+    for (int base = 0; base < n; base += 512) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int idx = base + i * 32 + lane;
+        best[16 + i] = idx < n ? buf[idx] : 0ull;
+      }
+      warp_sort_desc<32>(best, lane);
+    }
+  }
+  // element index of best[i] in lane l is i*32 + l
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < k) out[static_cast<size_t>(row) * k + idx] = best[i];
+  }
+}
+
+// entries -> (score, id) for retrieval in XB_COMPUTE_BF16 mode: score = exact fp32-accumulated dot of the
+// prepared (bf16) operands, recomputed here in fp32 so every entry has a deterministic score.
+__global__ void topk_emit_kernel(int Q, int k, int kp, int parts, const unsigned long long* __restrict__ ent,
+                                 const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ ip,
+                                 const long long* __restrict__ item_ids, long long id_base,
+                                 float* __restrict__ scores_tmp, long long* __restrict__ ids_tmp) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= Q * k) return;
+  const int qi = gw / k;
+  const unsigned long long e = ent[gw];
+  if (e == 0ull) {
+    if (lane == 0) { scores_tmp[gw] = -INFINITY; ids_tmp[gw] = -1; }
+    return;
+  }
+  const uint32_t col = ~static_cast<uint32_t>(e & 0xffffffffull);
+  const __nv_bfloat16* q = qp + static_cast<size_t>(qi) * parts * kp;
+  const __nv_bfloat16* v = ip + static_cast<size_t>(col) * parts * kp;
+  float acc = 0.f;
+  for (int kk = lane; kk < kp; kk += 32) acc = fmaf(prepped_val(q, kp, parts, kk), prepped_val(v, kp, parts, kk), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    scores_tmp[gw] = acc;
+    ids_tmp[gw] = item_ids != nullptr ? item_ids[col] : id_base + col;
+  }
+}
+
+// exact re-score for XB_COMPUTE_SPLIT: sequential-in-d fp64 sum of the ORIGINAL fp32 inputs, rounded
+// to fp32 once (the summation order the oracle defines, oracle/topk_oracle.c).  One thread per entry.
+template <typename T>
+__global__ void topk_rescore_kernel(int Q, int k, int d, const unsigned long long* __restrict__ ent,
+                                    const T* __restrict__ queries, const T* __restrict__ items,
+                                    const long long* __restrict__ item_ids, long long id_base,
+                                    float* __restrict__ scores_tmp, long long* __restrict__ ids_tmp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Q * k) return;
+  const int qi = g / k;
+  const unsigned long long e = ent[g];
+  if (e == 0ull) { scores_tmp[g] = -INFINITY; ids_tmp[g] = -1; return; }
+  const uint32_t col = ~static_cast<uint32_t>(e & 0xffffffffull);
+  const T* q = queries + static_cast<size_t>(qi) * d;
+  const T* v = items + static_cast<size_t>(col) * d;
+  double acc = 0.0;
+  for (int kk = 0; kk < d; ++kk) acc += static_cast<double>(static_cast<float>(q[kk])) * static_cast<double>(static_cast<float>(v[kk]));
+  scores_tmp[g] = static_cast<float>(acc);
+  ids_tmp[g] = item_ids != nullptr ? item_ids[col] : id_base + col;
+}
+
+// final ordering by (score desc, id asc) of L <= 1024 (score, id) pairs per row; emits the best k.
+// One warp per row.  Ids are compared as full int64 through a two-key sort: entries are ranked by a
+// 64-bit (score key, slot) sort after a stable pre-ordering by id is folded into the slot tie-break.
+__global__ void pairs_select_kernel(int Q, int L, int k, const float* __restrict__ scores,
+                                    const long long* __restrict__ ids, float* __restrict__ scores_out,
+                                    long long* __restrict__ ids_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= Q) return;
+  const float* s = scores + static_cast<size_t>(row) * L;
+  const long long* id = ids + static_cast<size_t>(row) * L;
+  // rank of an entry = number of entries that precede it in (score desc, id asc, slot asc) order.
+  // L is small (<= 1024): O(L^2 / 32) comparisons per lane is a few thousand.
+  for (int i = lane; i < L; i += 32) {
+    const float si = s[i];
+    const long long idi = id[i];
+    if (idi < 0) continue;  // empty slot
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float sj = s[j];
+      const long long idj = id[j];
+      if (idj < 0) continue;
+      const bool before = (sj > si) || (sj == si && (idj < idi || (idj == idi && j < i)));
+      rank += before ? 1 : 0;
+    }
+    if (rank < k) {
+      scores_out[static_cast<size_t>(row) * k + rank] = si;
+      ids_out[static_cast<size_t>(row) * k + rank] = idi;
+    }
+  }
+}
+
+__global__ void fill_topk_empty_kernel(size_t n, float* __restrict__ scores, long long* __restrict__ ids) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  scores[i] = -INFINITY;
+  ids[i] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Semi-hard mining, sparse path (0 < K < N), losses.py:134-162.  The sweep ranks columns with
+// tensor-core scores (bf16 / split-bf16 rounding), which can flip near-ties of the discontinuous
+// top-K selection.  So the sweep over-fetches Kf > K candidates per row and this kernel re-scores them
+// in fp32 from the original inputs, applies the reference's order exactly
+//   key = bits(R) ^ 0x7fffffff,  R = L_ij - L_ii   (semi-hard R<0 by R descending, then hard by R ascending)
+// and keeps the best K.  One warp per query row; Kf <= 96 (three candidates per lane).
+//   selcol[i][r] = chosen column of rank r (or -1), selL2[i][r] = its logit in log2 units.
+// ------------------------------------------------------------------------------------------------
+constexpr int MINE_SLOTS = 3;
+
+template <typename T>
+__global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int parts,
+                                     const unsigned long long* __restrict__ cand_sel,
+                                     const T* __restrict__ orig_q, const T* __restrict__ orig_i,
+                                     const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ ip,
+                                     const float4* __restrict__ qfwd, const float2* __restrict__ ipar,
+                                     const float4* __restrict__ rowinfo, const float* __restrict__ diag,
+                                     float sigma, int* __restrict__ selcol, float* __restrict__ selL2,
+                                     float4* __restrict__ rowstat, float* __restrict__ rowloss) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float4 qf = qfwd[row];
+  const float l2ii = rowinfo[row].w;
+  uint32_t key_[MINE_SLOTS];
+  int col_[MINE_SLOTS];
+  float l2_[MINE_SLOTS];
+#pragma unroll
+  for (int t = 0; t < MINE_SLOTS; ++t) { key_[t] = 0u; col_[t] = -1; l2_[t] = 0.f; }
+  // phase 1: exact logits of the candidates
+  for (int s = 0; s < Kf; ++s) {
+    const unsigned long long e = cand_sel[static_cast<size_t>(row) * Kf + s];
+    if (e == 0ull) continue;  // warp-uniform
+    const int col = static_cast<int>(~static_cast<uint32_t>(e & 0xffffffffull));
+    float acc = 0.f;
+    if (orig_q != nullptr) {
+      const T* q = orig_q + static_cast<size_t>(row) * d;
+      const T* v = orig_i + static_cast<size_t>(col) * d;
+      for (int kk = lane; kk < d; kk += 32) acc = fmaf(static_cast<float>(q[kk]), static_cast<float>(v[kk]), acc);
+    } else {
+      const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
+      const __nv_bfloat16* v = ip + static_cast<size_t>(col) * parts * kp;
+      for (int kk = lane; kk < kp; kk += 32)
+        acc = fmaf(prepped_val(q, kp, parts, kk), prepped_val(v, kp, parts, kk), acc);
+    }
+    acc = warp_sum(acc);
+    const float2 ipj = ipar[col];
+    const float l2 = fmaf(qf.x, acc + ipj.x, qf.y) - ipj.y;
+    const float r = (l2 - l2ii) + 0.0f;
+    uint32_t key = __float_as_uint(r) ^ 0x7fffffffu;
+    key = (r != r) ? 1u : max(key, 1u);
+    if ((s & 31) == lane) {
+#pragma unroll
+      for (int t = 0; t < MINE_SLOTS; ++t)
+        if ((s >> 5) == t) { key_[t] = key; col_[t] = col; l2_[t] = l2; }
+    }
+  }
+  // phase 2: rank = number of candidates ordered before this one (key desc, column asc)
+  int rank_[MINE_SLOTS];
+#pragma unroll
+  for (int t = 0; t < MINE_SLOTS; ++t) rank_[t] = 0;
+#pragma unroll
+  for (int tt = 0; tt < MINE_SLOTS; ++tt) {
+    for (int src = 0; src < 32; ++src) {
+      const uint32_t ok = __shfl_sync(0xffffffffu, key_[tt], src);
+      const int oc = __shfl_sync(0xffffffffu, col_[tt], src);
+      if (ok == 0u) continue;  // warp-uniform
+#pragma unroll
+      for (int t = 0; t < MINE_SLOTS; ++t)
+        rank_[t] += (ok > key_[t] || (ok == key_[t] && oc < col_[t])) ? 1 : 0;
+    }
+  }
+  for (int pos = lane; pos < K; pos += 32) selcol[static_cast<size_t>(row) * K + pos] = -1;
+  __syncwarp();
+  // phase 3: losses over the kept columns (losses.py:189-246, 342-346 restricted to the selection)
+  float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG;
+#pragma unroll
+  for (int t = 0; t < MINE_SLOTS; ++t) {
+    const bool keep = key_[t] != 0u && rank_[t] < K;
+    if (keep) {
+      selcol[static_cast<size_t>(row) * K + rank_[t]] = col_[t];
+      selL2[static_cast<size_t>(row) * K + rank_[t]] = l2_[t];
+      const float l2 = l2_[t];
+      cnt += 1.f;
+      csum += fmaxf(l2 + qf.w, 0.f);
+      const float x = l2 + qf.z;
+      hsum += fmaxf(x, 0.f);
+      lsum += x > 40.f ? x : log2f(1.f + exp2f(x));
+      mx = fmaxf(mx, l2);
+    } else {
+      key_[t] = 0u;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f;
+#pragma unroll
+  for (int t = 0; t < MINE_SLOTS; ++t)
+    if (key_[t] != 0u) se += exp2f(l2_[t] - mx);
+  cnt = warp_sum(cnt); csum = warp_sum(csum); hsum = warp_sum(hsum); lsum = warp_sum(lsum); se = warp_sum(se);
+  if (lane == 0) {
+    const float lseM2 = se > 0.f ? mx + log2f(se) : -INFINITY;
+    write_row_losses(row, B, sigma, rowinfo[row], diag[row], cnt, csum, hsum, lsum, lseM2, rowstat, rowloss);
+  }
+}
+
+// backward of the sparse path: accumulates acc_q[i] += G_ij v_j (plain stores; a warp owns its row),
+// acc_i[j] += G_ij q_i and the column sums of G with fp32 atomics; the dense finalisers then add the
+// diagonal terms.  acc_q / rs_q / acc_i / rs_i must be zeroed by the caller.
+__global__ void mined_backward_kernel(int B, int K, int kp, int parts, const int* __restrict__ selcol,
+                                      const float* __restrict__ selL2, const __nv_bfloat16* __restrict__ qp,
+                                      const __nv_bfloat16* __restrict__ ip, const float* __restrict__ u, float sigma,
+                                      const float4* __restrict__ qfwd, const float4* __restrict__ rowinfo,
+                                      const float4* __restrict__ rowstat, float* __restrict__ acc_q,
+                                      float* __restrict__ rs_q, float* __restrict__ acc_i, float* __restrict__ rs_i) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const GradCoef g = grad_coef(u, sigma, qfwd[row], rowinfo[row], rowstat[row]);
+  const float4 qf = qfwd[row];
+  const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
+  float rg = 0.f, rgh = 0.f;
+  for (int s = 0; s < K; ++s) {
+    const int col = selcol[static_cast<size_t>(row) * K + s];
+    if (col < 0) continue;
+    const float l2 = selL2[static_cast<size_t>(row) * K + s];
+    // l2 = base + r2 with base = a2*(S + c) - lq2; off_l are relative to base
+    const float base = l2 - qf.y;
+    float gv = 0.f, hv = 0.f;
+    gv += (base + g.offC) > 0.f ? g.kC : 0.f;
+    gv += g.kI * exp2f(base + g.offI);
+    gv += g.kM * exp2f(base + g.offM);
+    hv += (base + g.offH) > 0.f ? g.kH : 0.f;
+    hv += g.kL / (1.f + exp2f(-(base + g.offL)));
+    gv += hv;
+    rg += gv;
+    rgh += hv;
+    const __nv_bfloat16* v = ip + static_cast<size_t>(col) * parts * kp;
+    for (int kk = lane; kk < kp; kk += 32) {
+      acc_q[static_cast<size_t>(row) * kp + kk] += gv * prepped_val(v, kp, parts, kk);
+      atomicAdd(acc_i + static_cast<size_t>(col) * kp + kk, gv * prepped_val(q, kp, parts, kk));
+    }
+    if (lane == 0) atomicAdd(rs_i + static_cast<size_t>(col) * 2, gv);
+  }
+  if (lane == 0) {
+    rs_q[static_cast<size_t>(row) * 2] = rg;
+    rs_q[static_cast<size_t>(row) * 2 + 1] = rgh;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hashed embedding gather.  XXH32 of the 8 little-endian bytes of the id (xxhash.h, XXH32 for inputs
+// shorter than 16 bytes): h = seed + PRIME5 + 8; two 4-byte lanes; avalanche.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t xxh32_i64(long long id, uint32_t seed) {
+  const uint32_t P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+  const unsigned long long x = static_cast<unsigned long long>(id);
+  uint32_t h = seed + P5 + 8u;
+  const uint32_t w0 = static_cast<uint32_t>(x), w1 = static_cast<uint32_t>(x >> 32);
+  h += w0 * P3;
+  h = ((h << 17) | (h >> 15)) * P4;
+  h += w1 * P3;
+  h = ((h << 17) | (h >> 15)) * P4;
+  h ^= h >> 15;
+  h *= P2;
+  h ^= h >> 13;
+  h *= P3;
+  h ^= h >> 16;
+  return h;
+}
+
+__global__ void hash_indices_kernel(const long long* __restrict__ ids, long long n, int nh, uint32_t seed0,
+                                    uint32_t row_mask, int* __restrict__ idx_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * nh) return;
+  const long long r = i / nh;
+  const int h = static_cast<int>(i % nh);
+  idx_out[i] = static_cast<int>(xxh32_i64(ids[r], seed0 + h) & row_mask);
+}
+
+// `LPR` lanes cooperate on one id: each lane owns 8 bf16 (16 bytes) of the row per pass.
+// dim % 8 == 0.  Table rows are fetched with 128-bit read-only loads, the output row is written with
+// 128-bit streaming stores; the sum is fp32 with a single final rounding (embedding_bag(mode="sum")).
+__global__ void hash_gather_kernel(const long long* __restrict__ ids, long long n, int nh, uint32_t seed0,
+                                   const uint4* __restrict__ table, uint32_t row_mask, int dim,
+                                   uint4* __restrict__ out, int* __restrict__ idx_out, int lpr) {
+  const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long item = gt / lpr;
+  const int sub = static_cast<int>(gt % lpr);
+  if (item >= n) return;
+  const int vec_per_row = dim >> 3;
+  const long long id = ids[item];
+  for (int vcol = sub; vcol < vec_per_row; vcol += lpr) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int h = 0; h < nh; ++h) {
+      const uint32_t r = xxh32_i64(id, seed0 + h) & row_mask;
+      if (idx_out != nullptr && vcol == 0) idx_out[item * nh + h] = static_cast<int>(r);
+      const uint4 t = __ldg(table + static_cast<size_t>(r) * vec_per_row + vcol);
+      acc[0] += bf_lo(t.x); acc[1] += bf_hi(t.x);
+      acc[2] += bf_lo(t.y); acc[3] += bf_hi(t.y);
+      acc[4] += bf_lo(t.z); acc[5] += bf_hi(t.z);
+      acc[6] += bf_lo(t.w); acc[7] += bf_hi(t.w);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    __stcs(out + static_cast<size_t>(item) * vec_per_row + vcol, o);
+  }
+}
+
+__global__ void hash_scatter_grad_kernel(const long long* __restrict__ ids, long long n, int nh, uint32_t seed0,
+                                         const __nv_bfloat16* __restrict__ d_out, uint32_t row_mask, int dim,
+                                         float* __restrict__ d_table) {
+  const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long item = gt / dim;
+  const int c = static_cast<int>(gt % dim);
+  if (item >= n) return;
+  const float g = __bfloat162float(d_out[item * dim + c]);
+  const long long id = ids[item];
+  for (int h = 0; h < nh; ++h) {
+    const uint32_t r = xxh32_i64(id, seed0 + h) & row_mask;
+    atomicAdd(d_table + static_cast<size_t>(r) * dim + c, g);
+  }
+}
+
+}  // namespace xb

@@ -1,0 +1,637 @@
+// The score-tile "sweep" kernel: one CTA keeps a 128-row tile of the ROW operand resident in shared
+// memory and streams 128-row tiles of the COLUMN operand past it with TMA.  Each (row tile, column tile)
+// pair is one 128x128 score tile S = R . C^T computed by tcgen05.mma (bf16 in, fp32 accumulate) into a
+// double-buffered TMEM accumulator; four epilogue warps pull the tile out of TMEM with tcgen05.ld and
+// reduce it on the fly, so the B x N logit matrix of xfmr_rec/losses.py:9-12 never exists in HBM.
+//
+//   MODE_FWD   epilogue = masked per-row loss statistics (count, relu sums, softplus sum, online
+//              logsumexp)                                         -> losses.py:164-246, 325-346
+//   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile in shared memory, followed by a second
+//              tcgen05.mma  acc[128 x d] += G[128 x 128] . C_tile[128 x d]  (flash-style recompute).
+//              With (R,C) = (Q,I) acc is dQ; with (R,C) = (I,Q) the same kernel yields dI.
+//   MODE_TOPK  epilogue = streaming per-row top-k selection (retrieval, and the semi-hard negative
+//              mining order of losses.py:134-162)
+//   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (thread <-> TMEM lane <-> tile row).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace xb {
+
+constexpr int BM = 128;                  // tile rows  (UMMA M)
+constexpr int BN = 128;                  // tile cols  (UMMA N of the score MMA)
+constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
+constexpr int BLOCK_BYTES = 128 * 128;   // one [128 rows x 64 bf16] SWIZZLE_128B block
+constexpr int SWEEP_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_ACC_COL = 256;   // columns [256, 256+kp) hold the gradient accumulator
+constexpr int MAX_STAGES = 4;
+
+enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3 };
+
+// loss bits handled inside the sweep (AlignmentLoss is diagonal-only and never needs a sweep)
+enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 16, LM_ALL = 31 };
+
+__host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
+// floats of per-query gradient parameters: single loss {a2, off, k, 0}; all {a2, (off,k) x 5, 0}
+__host__ __device__ constexpr int grad_qpar_floats(int lm) { return lm_single(lm) ? 4 : 12; }
+
+constexpr float NEG_BIG = -1.0e30f;      // "no value yet" for running maxima (finite: avoids inf-inf)
+
+struct SweepParams {
+  int nR, nC;           // valid rows of the row / column operand
+  int nR_pad;           // nR rounded up to BM (row stride of per-chunk outputs)
+  int kp;               // padded embedding dim, multiple of 64, <= 256
+  int parts;            // 1 = bf16 operands; 2 = split (hi, lo) bf16 operands (fp32-grade scores)
+  int nstages;          // column-tile ring depth
+  int tiles_per_cta;    // column tiles swept by one CTA
+  int n_ctiles;         // ceil(nC / BN)
+  // FWD : rpar = float4 per query {a2, r2, xoff, sm2};            cpar = float2 per item {c, lq2}
+  // GRAD (QROW) : rpar = grad_qpar_floats per query;               cpar = float2 per item
+  // GRAD (!QROW): rpar = float2 per item;                          cpar = grad_qpar_floats per query
+  const float* rpar;
+  const float* cpar;
+  const uint32_t* mask; // [nR_pad][mask_words] bit (r, c) set => pair excluded (incl. c >= nC padding)
+  int mask_words;       // 32-bit words per mask row = 4 * n_ctiles
+  float* out_stats;     // FWD : [nchunks][nR_pad][8]   GRAD: [nchunks][nR_pad][2] (row sums of G)
+  float* out_acc;       // GRAD: [nchunks][nR_pad][kp] partial accumulators
+  float* dbg_s;         // DEBUG: [nR_pad][n_ctiles*BN] raw score tiles
+  // TOPK
+  unsigned long long* cand;  // [nchunks][nR_pad][cap] candidate entries (key << 32 | ~col)
+  int* cand_cnt;             // [nchunks][nR_pad]
+  int cap;                   // candidate buffer capacity per row (power of two, 64..1024)
+  int keep;                  // entries kept by a compaction (<= cap/2)
+  int topk_mining;           // 0: key = order(S)   1: key = bits(L2 - L2_ii) ^ 0x7fffffff (semi-hard order)
+};
+
+struct SweepSmemLayout {
+  uint32_t r_off, c_off, g_off, par_off, bar_off, total;
+};
+
+__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool has_g,
+                                                             int cpar_floats) {
+  SweepSmemLayout L;
+  const uint32_t tile = static_cast<uint32_t>(kp / KBLK) * parts * BLOCK_BYTES;
+  L.r_off = 0;
+  L.c_off = tile;
+  L.g_off = L.c_off + nstages * tile;
+  L.par_off = L.g_off + (has_g ? 2u * BLOCK_BYTES : 0u);
+  const uint32_t par_bytes = static_cast<uint32_t>(BN) * cpar_floats * 4u;  // column parameters of one tile
+  L.bar_off = L.par_off + par_bytes;
+  L.total = L.bar_off + 256u;  // barriers + tmem pointer
+  return L;
+}
+
+// Barrier slots inside the 256-byte barrier area.
+struct SweepBars {
+  uint64_t r_full;
+  uint64_t c_full[MAX_STAGES];
+  uint64_t c_empty[MAX_STAGES];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t g_full;
+  uint64_t g_empty;
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(SweepBars) <= 256, "barrier area overflow");
+
+// -------------------------------------------------------------------------------------------------
+// Per-element score -> logit in log2 units:  L2 = a2 * (S + c) + off - lq2
+//   a2  = sigma * sign(target) * log2(e)           (query side)
+//   c   = -|item|^2 / 2                             (item side)
+//   off = -a2 * |query|^2 / 2 (+ loss specific shift)
+//   lq2 = log2(e) * log_q[item]  (LogQ correction, optional)
+// -------------------------------------------------------------------------------------------------
+
+template <int LM>
+struct FwdState {
+  float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
+};
+
+template <int LM, bool LOGQ, bool MASKED>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, const float4 qp,
+                                          const float2* __restrict__ colp, FwdState<LM>& st) {
+  float L[32];
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    const float4 cp = *reinterpret_cast<const float4*>(colp + c);  // {c0, lq0, c1, lq1}, warp-broadcast
+    float l0 = fmaf(qp.x, __uint_as_float(v[c]) + cp.x, qp.y);
+    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]) + cp.z, qp.y);
+    if (LOGQ) {
+      l0 -= cp.y;
+      l1 -= cp.w;
+    }
+    if (MASKED) {
+      l0 = ((mw >> c) & 1u) ? -INFINITY : l0;
+      l1 = ((mw >> (c + 1)) & 1u) ? -INFINITY : l1;
+    }
+    L[c] = l0;
+    L[c + 1] = l1;
+  }
+  if (LM & (LM_INFONCE | LM_MINE)) {
+    float cm = L[0];
+#pragma unroll
+    for (int c = 1; c < 32; ++c) cm = fmaxf(cm, L[c]);
+    if (cm > st.mx) {
+      st.se *= ex2f(st.mx - cm);
+      st.mx = cm;
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      s0 += ex2f(L[c] - st.mx);
+      s1 += ex2f(L[c + 1] - st.mx);
+    }
+    st.se += s0 + s1;
+  }
+  if (LM & LM_CONTR) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      s0 += fmaxf(L[c] + qp.w, 0.f);
+      s1 += fmaxf(L[c + 1] + qp.w, 0.f);
+    }
+    st.csum += s0 + s1;
+  }
+  if (LM & (LM_HINGE | LM_LOGI)) {
+    float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float x0 = L[c] + qp.z, x1 = L[c + 1] + qp.z;
+      if (LM & LM_HINGE) {
+        h0 += fmaxf(x0, 0.f);
+        h1 += fmaxf(x1, 0.f);
+      }
+      if (LM & LM_LOGI) {
+        // softplus in log2 units: log2(1 + 2^x); for x > 40 it equals x to fp32 precision
+        g0 += x0 > 40.f ? x0 : lg2f(1.f + ex2f(x0));
+        g1 += x1 > 40.f ? x1 : lg2f(1.f + ex2f(x1));
+      }
+    }
+    st.hsum += h0 + h1;
+    st.lsum += g0 + g1;
+  }
+  st.cnt += static_cast<float>(32 - __popc(mw));
+}
+
+// Gradient element: g = sum_l k_l * phi_l(a2 * (S + c) + off_l - lq2)
+//   phi = 2^x (InfoNCE, MINE)   step(x > 0) (Contrastive, Hinge)   1 / (1 + 2^-x) (Logistic)
+// qp points at grad_qpar_floats(LM) floats: single {a2, off, k, 0}; all {a2, offC,kC, offI,kI, offM,kM,
+// offH,kH, offL,kL, 0}
+template <int LM, bool LOGQ>
+__device__ __forceinline__ void grad_elem(float S, float c_item, float lq2, const float* qp, float& g, float& h) {
+  // g = gradient of the non-pairwise losses, h = hinge + logistic part (needed separately for dL/dL_ii)
+  const float base = qp[0] * (S + c_item) - (LOGQ ? lq2 : 0.f);
+  g = 0.f;
+  h = 0.f;
+  if (lm_single(LM)) {
+    const float x = base + qp[1];
+    if (LM & (LM_INFONCE | LM_MINE)) g = qp[2] * ex2f(x);
+    if (LM & LM_CONTR) g = x > 0.f ? qp[2] : 0.f;
+    if (LM & LM_HINGE) h = x > 0.f ? qp[2] : 0.f;
+    if (LM & LM_LOGI) h = qp[2] * rcpf(1.f + ex2f(-x));
+  } else {
+    if (LM & LM_CONTR) g += (base + qp[1]) > 0.f ? qp[2] : 0.f;
+    if (LM & LM_INFONCE) g += qp[4] * ex2f(base + qp[3]);
+    if (LM & LM_MINE) g += qp[6] * ex2f(base + qp[5]);
+    if (LM & LM_HINGE) h += (base + qp[7]) > 0.f ? qp[8] : 0.f;
+    if (LM & LM_LOGI) h += qp[10] * rcpf(1.f + ex2f(-(base + qp[9])));
+  }
+}
+
+// Writes 32 consecutive bf16 values of tile row `row` (columns col0 .. col0+31, col0 % 32 == 0) into the
+// K-major SWIZZLE_128B G tile: block = col / 64, 16-byte chunk index XOR (row & 7).
+__device__ __forceinline__ void store_g_chunk(uint8_t* sG, int row, int col0, const uint32_t (&pk)[16]) {
+  uint8_t* base = sG + (col0 >> 6) * BLOCK_BYTES + row * 128;
+  const int chunk0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = (chunk0 + q) ^ (row & 7);
+    *reinterpret_cast<uint4*>(base + (chunk << 4)) =
+        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative descending sort of `cap` 64-bit entries held in a row's candidate buffer
+// (global memory, L2 resident).  After the call the buffer is sorted descending.
+// cap is a power of two in [64, 1024]; every lane holds cap/32 entries.
+// ------------------------------------------------------------------------------------------------
+template <int PER_LANE>
+__device__ __forceinline__ void warp_sort_desc(unsigned long long (&e)[PER_LANE], int lane) {
+  // element index of e[i] in lane l is  i * 32 + l  (striped => coalesced global access).
+  constexpr int N = PER_LANE * 32;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        // partner lives in the same lane, register index differs by j/32
+        const int dj = j >> 5;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          if ((i & dj) == 0) {
+            const int idx = i * 32 + lane;
+            const bool desc = (idx & k) == 0;  // descending blocks first => overall descending
+            unsigned long long a = e[i], b = e[i + dj];
+            const bool swap = desc ? (a < b) : (a > b);
+            e[i] = swap ? b : a;
+            e[i + dj] = swap ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int idx = i * 32 + lane;
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, e[i], j);
+          const bool desc = (idx & k) == 0;
+          const bool lower = (lane & j) == 0;  // this lane holds the lower index of the pair
+          const bool keep_max = (desc == lower);
+          e[i] = keep_max ? (e[i] > other ? e[i] : other) : (e[i] < other ? e[i] : other);
+        }
+      }
+    }
+  }
+}
+
+template <int PER_LANE>
+__device__ __forceinline__ void compact_row(unsigned long long* buf, int cnt, int lane) {
+  unsigned long long e[PER_LANE];
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int idx = i * 32 + lane;
+    e[i] = idx < cnt ? buf[idx] : 0ull;
+  }
+  warp_sort_desc<PER_LANE>(e, lane);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) buf[i * 32 + lane] = e[i];
+}
+
+__device__ __forceinline__ void compact_dispatch(unsigned long long* buf, int cnt, int cap, int lane) {
+  switch (cap) {
+    case 64: compact_row<2>(buf, cnt, lane); break;
+    case 128: compact_row<4>(buf, cnt, lane); break;
+    case 256: compact_row<8>(buf, cnt, lane); break;
+    case 512: compact_row<16>(buf, cnt, lane); break;
+    default: compact_row<32>(buf, cnt, lane); break;
+  }
+}
+
+// monotone map float -> uint32 (larger float => larger key); -inf -> small, NaN excluded upstream
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// =================================================================================================
+template <int MODE, int LM, bool QROW, bool LOGQ>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
+             const SweepParams p) {
+  constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
+  constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
+  constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
+
+  // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static smem here)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, HAS_G, CPAR);
+  uint8_t* sR = smem + lay.r_off;
+  uint8_t* sC = smem + lay.c_off;
+  uint8_t* sG = smem + lay.g_off;
+  float* sPar = reinterpret_cast<float*>(smem + lay.par_off);
+  SweepBars* bars = reinterpret_cast<SweepBars*>(smem + lay.bar_off);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_n = p.kp / KBLK;
+  const int nblk = kb_n * p.parts;
+  const uint32_t tile_bytes = static_cast<uint32_t>(nblk) * BLOCK_BYTES;
+  const int NS = p.nstages;
+
+  const int chunk = blockIdx.x;
+  const int rb = blockIdx.y;
+  const int t_begin = chunk * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.n_ctiles);
+  const int T = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->r_full, 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&bars->c_full[s], 1);
+      mbar_init(&bars->c_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->s_full[b], 1);
+      mbar_init(&bars->s_empty[b], EPI_THREADS);
+    }
+    mbar_init(&bars->g_full, EPI_THREADS);
+    mbar_init(&bars->g_empty, 1);
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer
+    if (lane == 0 && T > 0) {
+      mbar_arrive_expect_tx(&bars->r_full, tile_bytes);
+      for (int pt = 0; pt < p.parts; ++pt)
+        for (int kb = 0; kb < kb_n; ++kb)
+          tma_load_2d(sR + (pt * kb_n + kb) * BLOCK_BYTES, &tmR, &bars->r_full, pt * p.kp + kb * KBLK, rb * BM);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % NS;
+        mbar_wait(&bars->c_empty[s], ((t / NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes);
+        uint8_t* dst = sC + static_cast<size_t>(s) * tile_bytes;
+        for (int pt = 0; pt < p.parts; ++pt)
+          for (int kb = 0; kb < kb_n; ++kb)
+            tma_load_2d(dst + (pt * kb_n + kb) * BLOCK_BYTES, &tmC, &bars->c_full[s], pt * p.kp + kb * KBLK,
+                        (t_begin + t) * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0 && T > 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t idesc_g = umma_idesc_bf16(BM, static_cast<uint32_t>(p.kp), 0, 1);
+      const uint32_t sR_a = smem_u32(sR), sC_a = smem_u32(sC), sG_a = smem_u32(sG);
+
+      auto issue_scores = [&](int t) {
+        const int b = t & 1, s = t % NS;
+        mbar_wait(&bars->s_empty[b], ((t >> 1) & 1) ^ 1);
+        mbar_wait(&bars->c_full[s], (t / NS) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b) * BN;
+        const uint32_t c_base = sC_a + static_cast<uint32_t>(s) * tile_bytes;
+        uint32_t acc = 0;
+        // split operands: (lo x hi) + (hi x lo) + (hi x hi); the lo x lo term (2^-18 relative) is dropped
+        const int npairs = p.parts == 1 ? 1 : 3;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const int rp = (p.parts == 2 && pr == 0) ? 1 : 0;
+          const int cp = (p.parts == 2 && pr == 1) ? 1 : 0;
+          for (int kb = 0; kb < kb_n; ++kb) {
+            const uint32_t a_blk = sR_a + static_cast<uint32_t>(rp * kb_n + kb) * BLOCK_BYTES;
+            const uint32_t b_blk = c_base + static_cast<uint32_t>(cp * kb_n + kb) * BLOCK_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, umma_smem_desc(a_blk + k * 32, 16, 1024), umma_smem_desc(b_blk + k * 32, 16, 1024),
+                        idesc_s, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&bars->s_full[b]);
+        if (!HAS_G) umma_commit(&bars->c_empty[s]);
+      };
+
+      mbar_wait(&bars->r_full, 0);
+      issue_scores(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_scores(t + 1);
+        if (HAS_G) {
+          const int s = t % NS;
+          mbar_wait(&bars->g_full, t & 1);
+          tc_fence_after();
+          const uint32_t c_base = sC_a + static_cast<uint32_t>(s) * tile_bytes;
+#pragma unroll 1
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            // A = G tile, K-major (K = column index of the score tile)
+            const uint64_t da = umma_smem_desc(sG_a + (kk >> 2) * BLOCK_BYTES + (kk & 3) * 32, 16, 1024);
+            for (int pt = 0; pt < p.parts; ++pt) {
+              // B = column-operand tile read MN-major: N = embedding dim, K = tile row (16 rows = 2048 B)
+              const uint64_t db =
+                  umma_smem_desc(c_base + static_cast<uint32_t>(pt * kb_n) * BLOCK_BYTES + kk * 2048, BLOCK_BYTES, 1024);
+              umma_bf16(tmem_base + TMEM_ACC_COL, da, db, idesc_g, (t | kk | pt) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars->g_empty);
+          umma_commit(&bars->c_empty[s]);
+        }
+      }
+      if (HAS_G) umma_commit(&bars->acc_full);
+    }
+  } else if (T > 0) {
+    // ======================================================================== epilogue warps
+    const int quad = warp & 3;
+    const int row_l = quad * 32 + lane;             // tile row == TMEM lane
+    const int e_tid = threadIdx.x - 64;             // 0..127, used for cooperative parameter loads
+    const int row = rb * BM + row_l;
+    const bool row_ok = row < p.nR;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const size_t out_row = static_cast<size_t>(chunk) * p.nR_pad + row;
+
+    float rp_reg[RPAR];
+#pragma unroll
+    for (int i = 0; i < RPAR; ++i)
+      rp_reg[i] = (row_ok && p.rpar != nullptr) ? p.rpar[static_cast<size_t>(row) * RPAR + i] : 0.f;
+
+    const uint32_t* mrow = (p.mask != nullptr) ? p.mask + static_cast<size_t>(row) * p.mask_words : nullptr;
+
+    FwdState<LM> st;
+    float rg = 0.f, rgh = 0.f;                      // GRAD: row sums of G (all / hinge+logistic part)
+    // TOPK state
+    int cnt = 0;
+    uint32_t thr = row_ok ? 0u : 0xffffffffu;       // entries with key <= thr can no longer enter the top `keep`
+    unsigned long long* cbuf = nullptr;
+    if (MODE == MODE_TOPK) cbuf = p.cand + out_row * p.cap;
+
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      const int j0 = (t_begin + t) * BN;
+      // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
+      float* cpar_s = sPar;
+      if (t > 0) named_bar_sync(2, EPI_THREADS);
+      if (MODE == MODE_FWD || MODE == MODE_GRAD || (MODE == MODE_TOPK)) {
+        const int j = j0 + e_tid;
+        if (p.cpar != nullptr) {
+#pragma unroll
+          for (int i = 0; i < CPAR; ++i)
+            cpar_s[e_tid * CPAR + i] = (j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
+        }
+      }
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      if (mrow != nullptr) {
+        const uint4 m4 = *reinterpret_cast<const uint4*>(mrow + (j0 >> 5));
+        mw[0] = m4.x; mw[1] = m4.y; mw[2] = m4.z; mw[3] = m4.w;
+      } else {
+        // no mask given: only the column bound applies
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int rem = p.nC - (j0 + 32 * c);
+          mw[c] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+        }
+      }
+      named_bar_sync(1, EPI_THREADS);
+
+      mbar_wait(&bars->s_full[b], (t >> 1) & 1);
+      tc_fence_after();
+      if (HAS_G) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
+
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(b * BN + ch * 32), v);
+        tmem_ld_wait();
+        const uint32_t mwc = mw[ch];
+
+        if (MODE == MODE_FWD) {
+          const float4 qp = make_float4(rp_reg[0], rp_reg[1], rp_reg[2], rp_reg[3]);
+          const float2* colp = reinterpret_cast<const float2*>(cpar_s) + ch * 32;
+          if (__any_sync(0xffffffffu, mwc != 0u)) fwd_chunk<LM, LOGQ, true>(v, mwc, qp, colp, st);
+          else fwd_chunk<LM, LOGQ, false>(v, mwc, qp, colp, st);
+        } else if (MODE == MODE_GRAD) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float g[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = ch * 32 + c + u;
+              const float S = __uint_as_float(v[c + u]);
+              float gv, hv;
+              if (QROW) {
+                const float2 ip = *reinterpret_cast<const float2*>(cpar_s + col * 2);
+                grad_elem<LM, LOGQ>(S, ip.x, ip.y, rp_reg, gv, hv);
+              } else {
+                float qp[grad_qpar_floats(LM)];
+                const float4* q4 = reinterpret_cast<const float4*>(cpar_s + col * CPAR);
+#pragma unroll
+                for (int i = 0; i < CPAR / 4; ++i) {
+                  const float4 x = q4[i];
+                  qp[4 * i] = x.x; qp[4 * i + 1] = x.y; qp[4 * i + 2] = x.z; qp[4 * i + 3] = x.w;
+                }
+                grad_elem<LM, LOGQ>(S, rp_reg[0], rp_reg[1], qp, gv, hv);
+              }
+              const bool masked = (mwc >> (c + u)) & 1u;
+              hv = masked ? 0.f : hv;
+              gv = masked ? 0.f : gv + hv;
+              rgh += hv;
+              g[u] = gv;
+            }
+            rg += g[0] + g[1];
+            pk[c >> 1] = pack_bf16x2(g[0], g[1]);
+          }
+          store_g_chunk(sG, row_l, ch * 32, pk);
+        } else if (MODE == MODE_DEBUG) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float a = __uint_as_float(v[c]), bb = __uint_as_float(v[c + 1]);
+            if (p.dbg_s != nullptr) {
+              float* d = p.dbg_s + static_cast<size_t>(row) * (static_cast<size_t>(p.n_ctiles) * BN) + j0 + ch * 32 + c;
+              d[0] = a;
+              d[1] = bb;
+            }
+            a = ((mwc >> c) & 1u) ? 0.f : a;
+            bb = ((mwc >> (c + 1)) & 1u) ? 0.f : bb;
+            rg += a + bb;
+            pk[c >> 1] = pack_bf16x2(a, bb);
+          }
+          store_g_chunk(sG, row_l, ch * 32, pk);
+        } else if (MODE == MODE_TOPK) {
+          // key per element (larger = better); masked / out-of-range columns get key 0
+          uint32_t key[32];
+          uint32_t kmax = 0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float S = __uint_as_float(v[c]);
+            uint32_t k;
+            if (p.topk_mining) {
+              const float2 ip = *reinterpret_cast<const float2*>(cpar_s + (ch * 32 + c) * 2);
+              float l2 = fmaf(rp_reg[0], S + ip.x, rp_reg[1]);
+              if (LOGQ) l2 -= ip.y;
+              const float r = (l2 + rp_reg[2]) + 0.0f;       // rp_reg[2] = -L2_ii: R = L_ij - L_ii; -0 -> +0
+              k = __float_as_uint(r) ^ 0x7fffffffu;           // semi-hard (R<0, desc) before hard (R>=0, asc)
+              k = (r != r) ? 1u : max(k, 1u);
+            } else {
+              k = (S != S) ? 1u : max(order_key(S), 1u);
+            }
+            k = ((mwc >> c) & 1u) ? 0u : k;
+            key[c] = k;
+            kmax = max(kmax, k);
+          }
+          if (kmax > thr) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (key[c] > thr) {
+                const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
+                cbuf[cnt++] = (static_cast<unsigned long long>(key[c]) << 32) | static_cast<uint32_t>(~col);
+              }
+            }
+          }
+          // compaction: any row whose buffer cannot absorb another 32 candidates is sorted by its
+          // warp and truncated to the best `keep`; thr becomes the key of the last kept entry - 1.
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
+            const int n = __shfl_sync(0xffffffffu, cnt, src);
+            __syncwarp();
+            compact_dispatch(buf, n, p.cap, lane);
+            __syncwarp();
+            const unsigned long long last = buf[p.keep - 1];
+            if (lane == src) {
+              cnt = p.keep;
+              const uint32_t kth = static_cast<uint32_t>(last >> 32);
+              thr = kth > 0 ? kth - 1 : 0;   // keys equal to the k-th stay eligible (lower column wins ties)
+            }
+          }
+        }
+      }
+      // accumulator buffer b fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&bars->s_empty[b]);
+      if (HAS_G) {
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->g_full);
+      }
+    }
+
+    // ----------------------------------------------------------------------- unit epilogue
+    if (MODE == MODE_FWD) {
+      float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
+      o[0] = make_float4(st.cnt, st.csum, st.hsum, st.lsum);
+      o[1] = make_float4(st.mx, st.se, 0.f, 0.f);
+    }
+    if (HAS_G) {
+      mbar_wait(&bars->acc_full, 0);
+      tc_fence_after();
+      float* o = p.out_acc + out_row * p.kp;
+      for (int cc = 0; cc < p.kp / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + TMEM_ACC_COL + static_cast<uint32_t>(cc * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<uint4*>(o + cc * 32 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+      *reinterpret_cast<float2*>(p.out_stats + out_row * 2) = make_float2(rg, rgh);
+    }
+    if (MODE == MODE_TOPK) {
+      p.cand_cnt[out_row] = cnt;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace xb

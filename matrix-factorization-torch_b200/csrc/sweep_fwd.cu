@@ -1,0 +1,19 @@
+#include "sweep_launch.h"
+namespace xb {
+#define XB_FWD_CASE(LMV)                                                                                   \
+  case LMV:                                                                                                \
+    return logq ? launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, true>, tmR, tmC, p, grid, smem, st)  \
+                : launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, false>, tmR, tmC, p, grid, smem, st);
+cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+                             const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (lm) {
+    XB_FWD_CASE(LM_CONTR)
+    XB_FWD_CASE(LM_INFONCE)
+    XB_FWD_CASE(LM_MINE)
+    XB_FWD_CASE(LM_HINGE)
+    XB_FWD_CASE(LM_LOGI)
+    XB_FWD_CASE(LM_ALL)
+    default: return cudaErrorInvalidValue;
+  }
+}
+}  // namespace xb

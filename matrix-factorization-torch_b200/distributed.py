@@ -1,0 +1,143 @@
+"""Sharding of the score path across the GPUs of one box (``torch.distributed``, NCCL over NVLink).
+
+The reference has no collective of its own (Lightning DDP with one worker, ``xfmr_rec/ray.py:40, 106``);
+both functions here are the north-star extensions specified in SURVEY.md 8(e):
+
+* training — ``global_negatives_losses``: every rank all-gathers the other ranks' in-batch items and
+  uniform negatives and scores its own users against the union.  The gathered rows are re-ordered so
+  that the rank's own positives stay in rows ``0..B-1``; that keeps every convention of
+  ``xfmr_rec/losses.py`` (diagonal = positive, ``item_idx[:B]`` = in-batch ids) and makes the oracle
+  literally "the reference loss called once per rank on the re-ordered concatenation".  Gradients of
+  the gathered rows flow back to their owners through a sum-reduction (reduce-scatter).
+* retrieval — ``sharded_topk``: the catalog is row-sharded, queries are replicated, each rank returns
+  its local top-k and the ``[G, Q, k]`` candidates are merged with the (score desc, id asc)
+  comparator, which is deterministic for any G.
+
+Host logic only; the loss / search callables are injected so the CPU (gloo) tests can drive the
+same code with the oracle.
+"""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING
+
+import torch
+import torch.distributed as dist
+
+if TYPE_CHECKING:
+    from collections.abc import Callable
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """All-gather of equally-shaped row blocks; backward sum-reduces each block to its owner."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group) -> torch.Tensor:  # noqa: ANN001
+        world = dist.get_world_size(group)
+        ctx.group = group
+        ctx.rows = x.size(0)
+        out = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(out, x.contiguous(), group=group)
+        return torch.stack(out)  # [G, rows, d]
+
+    @staticmethod
+    def backward(ctx, grad: torch.Tensor):  # noqa: ANN001, ANN205
+        group = ctx.group
+        rank = dist.get_rank(group)
+        grad = grad.contiguous()
+        if dist.get_backend(group) == "nccl":
+            out = torch.empty_like(grad[0])
+            dist.reduce_scatter_tensor(out, grad.reshape(-1, *grad.shape[2:]), group=group)
+            return out, None
+        # gloo has no reduce-scatter: all-reduce and keep the own slice
+        dist.all_reduce(grad, group=group)
+        return grad[rank].clone(), None
+
+
+def _gather_plain(x: torch.Tensor, group) -> torch.Tensor:  # noqa: ANN001
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(out, x.contiguous(), group=group)
+    return torch.stack(out)
+
+
+def _own_first(stacked: torch.Tensor, rank: int) -> torch.Tensor:
+    """[G, rows, ...] -> [G*rows, ...] with block `rank` first, the others in rank order."""
+    world = stacked.size(0)
+    order = [rank] + [r for r in range(world) if r != rank]
+    return torch.cat([stacked[r] for r in order], dim=0)
+
+
+def global_negatives_inputs(
+    item_embed: torch.Tensor,
+    neg_embed: torch.Tensor,
+    item_idx: torch.Tensor,
+    neg_idx: torch.Tensor,
+    *,
+    log_q_item: torch.Tensor | None = None,
+    log_q_neg: torch.Tensor | None = None,
+    group=None,  # noqa: ANN001
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor | None]:
+    """Candidate set of this rank: ``[own items | other ranks' items | all ranks' negatives]``.
+
+    Returns ``(item_embed_all [G*(B+U), d], item_idx_all, log_q_all)``; differentiable in
+    ``item_embed`` and ``neg_embed`` (gradient contributions from every rank are summed at the owner).
+    Mirrors the single-rank concatenation of ``xfmr_rec/lightning.py:125-135``.
+    """
+    rank = dist.get_rank(group)
+    items = _own_first(_AllGatherRows.apply(item_embed, group), rank)
+    negs = _own_first(_AllGatherRows.apply(neg_embed, group), rank)
+    idx_items = _own_first(_gather_plain(item_idx, group), rank)
+    idx_negs = _own_first(_gather_plain(neg_idx, group), rank)
+    log_q = None
+    if log_q_item is not None and log_q_neg is not None:
+        log_q = torch.cat(
+            [_own_first(_gather_plain(log_q_item, group), rank), _own_first(_gather_plain(log_q_neg, group), rank)]
+        )
+    return torch.cat([items, negs], dim=0), torch.cat([idx_items, idx_negs], dim=0), log_q
+
+
+def global_negatives_losses(
+    loss_fn: Callable[..., torch.Tensor],
+    user_embed: torch.Tensor,
+    item_embed: torch.Tensor,
+    neg_embed: torch.Tensor,
+    target: torch.Tensor,
+    *,
+    item_idx: torch.Tensor,
+    neg_idx: torch.Tensor,
+    pos_idx: torch.Tensor,
+    group=None,  # noqa: ANN001
+    **loss_kwargs,  # noqa: ANN003
+) -> torch.Tensor:
+    """Per-rank loss against the global candidate set; the job's loss is the sum over ranks.
+
+    ``loss_fn(user_embed, item_embed_all, target, item_idx=, pos_idx=, **loss_kwargs)`` is any of the
+    drop-in modules / ``fused_losses`` (or the oracle in CPU tests).
+    """
+    items_all, idx_all, _ = global_negatives_inputs(item_embed, neg_embed, item_idx, neg_idx, group=group)
+    return loss_fn(user_embed, items_all, target, item_idx=idx_all, pos_idx=pos_idx, **loss_kwargs)
+
+
+def sharded_topk(
+    search_fn: Callable[[torch.Tensor, int], tuple[torch.Tensor, torch.Tensor]],
+    merge_fn: Callable[[torch.Tensor, torch.Tensor, int], tuple[torch.Tensor, torch.Tensor]],
+    queries: torch.Tensor,
+    k: int,
+    *,
+    group=None,  # noqa: ANN001
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """Row-sharded catalog search: local top-k on every rank, all-gather, k-way merge.
+
+    ``search_fn(queries, k) -> (scores [Q, k], global ids [Q, k])`` searches the local shard (e.g.
+    ``ItemProcessor.search_batch`` with ``item_ids`` / ``id_base`` carrying global ids);
+    ``merge_fn(scores [Q, G*k], ids [Q, G*k], k)`` is ``retrieval.topk_merge`` on GPU.  Every rank ends up
+    with the full result.
+    """
+    scores, ids = search_fn(queries, k)
+    all_scores = _gather_plain(scores, group)  # [G, Q, k]
+    all_ids = _gather_plain(ids, group)
+    world = all_scores.size(0)
+    cat_scores = all_scores.permute(1, 0, 2).reshape(scores.size(0), world * k)
+    cat_ids = all_ids.permute(1, 0, 2).reshape(ids.size(0), world * k)
+    return merge_fn(cat_scores, cat_ids, k)

@@ -1,0 +1,256 @@
+"""Exact top-k retrieval with the call shape of ``ItemProcessor.search``.
+
+Reference: ``xfmr_rec/data/lightning.py:182-259``.  The reference builds a LanceDB ``IVF_HNSW_PQ``
+cosine index (``get_index``, :182-235) and answers one query at a time with an approximate search,
+removing ``exclude_item_ids`` before ranking (``prefilter=True``, :247-252) and reporting
+``score = 1 - cosine_distance`` (:257).  Here the index is the embedding matrix itself, resident in HBM
+in the layout the TMA descriptors read, and ``search`` is an exact brute-force scan on the tensor cores:
+same arguments, same result columns, batched over queries.
+
+Ordering contract: score descending, ties broken by the lower item id.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import TYPE_CHECKING
+
+import torch
+
+from . import _lib
+
+if TYPE_CHECKING:
+    from collections.abc import Sequence
+
+    import pandas as pd
+
+TOP_K = 20  # xfmr_rec/params.py:21
+_PAD_ID = -(2**63)  # never a real id; ignored by the mask builder
+
+
+def build_pair_mask(
+    col_ids: torch.Tensor,
+    row_id_lists: torch.Tensor | None,
+    *,
+    row_ids0: torch.Tensor | None = None,
+    num_rows: int | None = None,
+    transpose: bool = False,
+) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """Bit (r, c) set iff ``col_ids[c] == row_ids0[r]`` or ``col_ids[c] in row_id_lists[r]``.
+
+    Returns ``(mask, mask_t)`` as uint32 bit matrices padded to 128 rows / 128 columns
+    (``xb_build_pair_mask``).  This is the complement of ``negative_masks`` (losses.py:92-110) and the
+    ``NOT IN`` prefilter of ``search`` (data/lightning.py:247-252).
+    """
+    device = _lib.require_cuda(col_ids, row_id_lists, row_ids0)
+    num_cols = col_ids.numel()
+    if row_id_lists is not None:
+        num_rows = row_id_lists.size(0)
+        list_len = row_id_lists.size(1)
+        row_id_lists = row_id_lists.to(torch.int64).contiguous()
+    else:
+        list_len = 0
+    if row_ids0 is not None:
+        num_rows = row_ids0.numel()
+        row_ids0 = row_ids0.to(torch.int64).contiguous()
+    if num_rows is None:
+        msg = "num_rows is unknown: give row_id_lists, row_ids0 or num_rows"
+        raise ValueError(msg)
+    col_ids = col_ids.to(torch.int64).contiguous()
+    rows_pad = -(-num_rows // 128) * 128
+    cols_pad = -(-num_cols // 128) * 128
+    words = _lib.lib.xb_mask_words(num_cols)
+    words_t = _lib.lib.xb_mask_words(num_rows)
+    with torch.cuda.device(device):
+        mask = torch.empty(rows_pad, words, dtype=torch.int32, device=device)
+        mask_t = torch.empty(cols_pad, words_t, dtype=torch.int32, device=device) if transpose else None
+        ws_bytes = int(_lib.lib.xb_pair_mask_workspace_bytes(num_cols))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        status = _lib.lib.xb_build_pair_mask(
+            num_rows,
+            num_cols,
+            list_len,
+            col_ids.data_ptr(),
+            _lib.ptr(row_ids0),
+            _lib.ptr(row_id_lists) if list_len else None,
+            mask.data_ptr(),
+            _lib.ptr(mask_t),
+            ws.data_ptr(),
+            ws_bytes,
+            _lib.stream_ptr(device),
+        )
+    _lib.check(status, "xb_build_pair_mask")
+    return mask, mask_t
+
+
+def topk_search(
+    queries: torch.Tensor,
+    items: torch.Tensor,
+    k: int,
+    *,
+    item_ids: torch.Tensor | None = None,
+    id_base: int = 0,
+    excl_mask: torch.Tensor | None = None,
+    compute: str | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """``(scores [Q, k] fp32, ids [Q, k] int64)`` of the k best catalog rows per query (``xb_topk_search``)."""
+    device = _lib.require_cuda(queries, items, item_ids, excl_mask)
+    if queries.dim() != 2 or items.dim() != 2 or queries.size(1) != items.size(1):  # noqa: PLR2004
+        msg = f"queries {tuple(queries.shape)} and items {tuple(items.shape)} must be [Q, d] and [N, d]"
+        raise ValueError(msg)
+    if items.dtype != queries.dtype:
+        queries = queries.to(items.dtype)
+    queries = queries.contiguous()
+    items = items.contiguous()
+    desc = _lib.TopkDesc(
+        num_queries=queries.size(0),
+        num_items=items.size(0),
+        dim=queries.size(1),
+        k=k,
+        in_dtype=_lib.dtype_code(items.dtype),
+        compute=_lib.compute_code(compute, items.dtype),
+        has_exclusions=int(excl_mask is not None),
+        reserved=0,
+        id_base=id_base,
+    )
+    ws_bytes = int(_lib.lib.xb_topk_workspace_bytes(ctypes.byref(desc)))
+    if ws_bytes == 0:
+        raise _lib.XbError("xb_topk_workspace_bytes: " + _lib.lib.xb_last_error_string().decode())
+    if item_ids is not None:
+        item_ids = item_ids.to(torch.int64).contiguous()
+    with torch.cuda.device(device):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        scores = torch.empty(queries.size(0), k, dtype=torch.float32, device=device)
+        ids = torch.empty(queries.size(0), k, dtype=torch.int64, device=device)
+        status = _lib.lib.xb_topk_search(
+            ctypes.byref(desc),
+            queries.data_ptr(),
+            items.data_ptr(),
+            _lib.ptr(item_ids),
+            _lib.ptr(excl_mask),
+            scores.data_ptr(),
+            ids.data_ptr(),
+            ws.data_ptr(),
+            ws_bytes,
+            _lib.stream_ptr(device),
+        )
+    _lib.check(status, "xb_topk_search")
+    return scores, ids
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Merge ``[Q, L]`` candidate (score, id) lists into the k best by (score desc, id asc)."""
+    device = _lib.require_cuda(scores, ids)
+    scores = scores.to(torch.float32).contiguous()
+    ids = ids.to(torch.int64).contiguous()
+    num_queries, length = scores.shape
+    with torch.cuda.device(device):
+        out_s = torch.empty(num_queries, k, dtype=torch.float32, device=device)
+        out_i = torch.empty(num_queries, k, dtype=torch.int64, device=device)
+        status = _lib.lib.xb_topk_merge(
+            num_queries, 1, length, k, scores.data_ptr(), ids.data_ptr(), out_s.data_ptr(), out_i.data_ptr(),
+            _lib.stream_ptr(device),
+        )
+    _lib.check(status, "xb_topk_merge")
+    return out_s, out_i
+
+
+class ItemProcessor:
+    """Exact-search stand-in for ``xfmr_rec.data.lightning.ItemProcessor`` (search side only).
+
+    ``get_index`` takes the item embeddings directly (the reference encodes them with the model,
+    data/lightning.py:182-219, which is outside this path) and keeps them on the GPU; ``search`` has the
+    reference's signature and returns the same columns (``id_col``, ``text_col``, ``score``).
+    """
+
+    def __init__(self, *, id_col: str = "movie_id", text_col: str = "movie_text", compute: str | None = None) -> None:
+        self.id_col = id_col
+        self.text_col = text_col
+        self.compute = compute
+        self.embeddings: torch.Tensor | None = None
+        self.item_ids: torch.Tensor | None = None
+        self.item_text: Sequence[str] | None = None
+
+    def get_index(
+        self,
+        item_embeddings: torch.Tensor,
+        item_ids: torch.Tensor | Sequence[int] | None = None,
+        item_text: Sequence[str] | None = None,
+        *,
+        device: torch.device | str = "cuda",
+    ) -> ItemProcessor:
+        emb = torch.as_tensor(item_embeddings)
+        if emb.dtype not in (torch.float32, torch.bfloat16):
+            emb = emb.float()
+        self.embeddings = emb.to(device).contiguous()
+        if item_ids is None:
+            self.item_ids = None
+        else:
+            self.item_ids = torch.as_tensor(item_ids, dtype=torch.int64).to(device).contiguous()
+        self.item_text = item_text
+        return self
+
+    def _exclusion_mask(self, exclude: torch.Tensor | Sequence[Sequence[int]] | None, num_queries: int) -> torch.Tensor | None:
+        if exclude is None:
+            return None
+        assert self.embeddings is not None
+        device = self.embeddings.device
+        if not isinstance(exclude, torch.Tensor):
+            width = max((len(e) for e in exclude), default=0)
+            if width == 0:
+                return None
+            rows = [list(e) + [_PAD_ID] * (width - len(e)) for e in exclude]
+            exclude = torch.tensor(rows, dtype=torch.int64)
+        if exclude.numel() == 0:
+            return None
+        if exclude.size(0) != num_queries:
+            msg = f"one exclusion list per query expected: {exclude.size(0)} lists for {num_queries} queries"
+            raise ValueError(msg)
+        col_ids = self.item_ids
+        if col_ids is None:
+            col_ids = torch.arange(self.embeddings.size(0), dtype=torch.int64, device=device)
+        mask, _ = build_pair_mask(col_ids, exclude.to(device))
+        return mask
+
+    def search_batch(
+        self,
+        embedding: torch.Tensor,
+        exclude_item_ids: torch.Tensor | Sequence[Sequence[int]] | None = None,
+        top_k: int = TOP_K,
+    ) -> tuple[torch.Tensor, torch.Tensor]:
+        """Batched search: ``embedding [Q, d]`` -> ``(scores [Q, k], item ids [Q, k])`` on the GPU."""
+        if self.embeddings is None:
+            msg = "index is empty: call get_index first"
+            raise RuntimeError(msg)
+        queries = torch.as_tensor(embedding)
+        if queries.dim() == 1:
+            queries = queries[None, :]
+        queries = queries.to(self.embeddings.device)
+        mask = self._exclusion_mask(exclude_item_ids, queries.size(0))
+        return topk_search(
+            queries, self.embeddings, top_k, item_ids=self.item_ids, excl_mask=mask, compute=self.compute
+        )
+
+    def search(
+        self,
+        embedding,  # noqa: ANN001  numpy [d] / [1, d] or tensor, as in the reference
+        exclude_item_ids: list[int] | None = None,
+        top_k: int = TOP_K,
+    ) -> pd.DataFrame:
+        """One query -> DataFrame sorted by score (data/lightning.py:237-259)."""
+        import pandas as pd  # noqa: PLC0415
+
+        exclude = [list(exclude_item_ids)] if exclude_item_ids else None
+        scores, ids = self.search_batch(torch.as_tensor(embedding).reshape(1, -1), exclude, top_k)
+        scores = scores[0].cpu()
+        ids = ids[0].cpu()
+        keep = ids >= 0
+        frame = {self.id_col: ids[keep].numpy(), "score": scores[keep].numpy()}
+        if self.item_text is not None:
+            if self.item_ids is None:
+                rows = ids[keep].tolist()
+            else:
+                lookup = {int(v): r for r, v in enumerate(self.item_ids.cpu().tolist())}
+                rows = [lookup[int(v)] for v in ids[keep].tolist()]
+            frame[self.text_col] = [self.item_text[r] for r in rows]
+        return pd.DataFrame(frame)
