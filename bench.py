@@ -1,0 +1,450 @@
+"""Benchmark of the B200 score path.  ``python bench.py --gpus N --steps K --warmup W``.
+
+Headline metric (BASELINE.json): **fused loss forward+backward samples/s** on config 2 — MovieLens-32M
+shaped, batch 4,096 x 87,585 candidate items, d=128, bf16, P=32 — for the sampled-softmax loss
+(``InfomationNoiseContrastiveEstimationLoss``); the other six losses, the exact top-100 retrieval rate
+(the second half of BASELINE.json's metric) and the hash-gather bandwidth ride along as extra keys of the
+same JSON line.
+
+A "step" is one pass of the hot path over one synthetic batch: ``loss(user_embed, item_embed, target,
+item_idx=, pos_idx=)`` + ``backward()`` through the drop-in module, i.e. through the C ABI.
+``value`` times the steps with device-resident inputs; ``e2e`` times the same call with HOST inputs
+(pinned), copying them to the device and reading the loss back inside the timed region.
+
+N > 1 (torchrun, one rank per GPU): the loss path shards by users with no data-path collective at this
+config (every rank scores its own 4,096 users), so ``value`` = N x 4,096 / max-over-ranks time, "weak"
+scaling; the catalog-sharded retrieval extra uses NCCL for the top-k merge.
+
+``--impl reference`` times the CPU port of the reference algorithm (``oracle/losses_oracle.py``; the
+reference itself is Python and is not present on the GPU box) on the host cores of rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "fused_loss_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+C2 = {"batch": 4096, "num_items": 87585, "dim": 128, "num_pos": 32}
+HEADLINE_LOSS = "InfomationNoiseContrastiveEstimationLoss"
+SIGMA, MARGIN = 5.0, 0.5
+
+
+def peaks() -> dict:
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        data = json.loads(path.read_text())
+        return {"hbm_gbs": data["hbm_gbs"], "bf16_tflops": data["bf16_tflops"],
+                "bf16_tflops_sustained": data.get("bf16_tflops_sustained", data["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = pathlib.Path(f"/tmp/xb_clocks_{os.getpid()}.csv")  # noqa: S108
+        self.t_begin = 0.0
+        self.t_end = 0.0
+
+    def start(self) -> None:
+        """Start sampling; nvidia-smi needs a moment before its first line, so call this ahead of the region."""
+        try:
+            self.proc = subprocess.Popen(  # noqa: S603
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",  # noqa: S607
+                 "-i", str(self.gpu_index)],
+                stdout=self.path.open("w"), stderr=subprocess.DEVNULL,
+            )
+        except OSError:
+            self.proc = None
+
+    def mark_begin(self) -> None:
+        self.t_begin = time.time()
+
+    def mark_end(self) -> None:
+        self.t_end = time.time()
+
+    def stop(self) -> None:
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+
+    def summary(self) -> dict:
+        """Median SM clock and the throttle reasons seen INSIDE [mark_begin, mark_end] (+- one sample)."""
+        import datetime  # noqa: PLC0415
+
+        sm, mx, reasons = [], [], set()
+        if self.path.exists():
+            for line in self.path.read_text().splitlines():
+                cols = [c.strip() for c in line.split(",")]
+                if len(cols) < 9:  # noqa: PLR2004
+                    continue
+                try:
+                    stamp = datetime.datetime.strptime(cols[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()  # noqa: DTZ007
+                    if not (self.t_begin - 0.06 <= stamp <= self.t_end + 0.06):  # noqa: PLR2004
+                        continue
+                    sm.append(float(cols[1]))
+                    mx.append(float(cols[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), cols[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            self.path.unlink(missing_ok=True)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flush_l2(buf: torch.Tensor) -> None:
+    buf.add_(1)  # 256 MiB read + write > 126 MB of L2
+
+
+def timed_steps(step_fn, steps: int, warmup: int, flush_buf: torch.Tensor | None) -> list[float]:  # noqa: ANN001
+    """Per-step device milliseconds (CUDA events on the current stream); L2 flushed between steps."""
+    for _ in range(warmup):
+        if flush_buf is not None:
+            flush_l2(flush_buf)
+        step_fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(steps):
+        if flush_buf is not None:
+            flush_l2(flush_buf)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_fn()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return times
+
+
+def make_c2(device: torch.device, seed: int, dtype: torch.dtype) -> dict:
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    inp = synthetic.make_loss_inputs(C2["batch"], C2["num_items"], C2["dim"], C2["num_pos"], n_catalog=C2["num_items"],
+                                     seed=seed, device=device)
+    inp["user_embed"] = inp["user_embed"].to(dtype)
+    inp["item_embed"] = inp["item_embed"].to(dtype)
+    return inp
+
+
+def loss_step_fn(module, inp: dict):  # noqa: ANN001, ANN201
+    q = inp["user_embed"].detach().requires_grad_(True)
+    v = inp["item_embed"].detach().requires_grad_(True)
+
+    def step() -> torch.Tensor:
+        q.grad = None
+        v.grad = None
+        loss = module(q, v, inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
+        loss.backward()
+        return loss
+
+    return step
+
+
+def cpu_reference_rate(steps: int, warmup: int, name: str = HEADLINE_LOSS) -> dict:
+    """The reference's algorithm (CPU port) on the host cores: fwd + autograd.grad on a bounded sample of C2:
+    full batch, the first N_s candidate columns (the B x N x P accidental-hit broadcast of losses.py:108 is
+    11.5 GB at full N), extrapolated linearly in N to the full candidate count."""
+    from oracle import losses_oracle  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_sample = 8192
+    inp = synthetic.make_loss_inputs(C2["batch"], n_sample, C2["dim"], C2["num_pos"], n_catalog=C2["num_items"], seed=0)
+
+    def run() -> float:
+        t0 = time.perf_counter()
+        losses_oracle.losses_and_grads(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"],
+                                       pos_idx=inp["pos_idx"], sigma=SIGMA, margin=MARGIN, names=(name,))
+        return time.perf_counter() - t0
+
+    for _ in range(max(warmup, 1)):
+        run()
+    times = [run() for _ in range(max(steps, 1))]
+    best = min(times)
+    scale = C2["num_items"] / n_sample
+    return {
+        "value": C2["batch"] / (best * scale),
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": (f"{name} fwd+bwd, B={C2['batch']} x N_s={n_sample} of {C2['num_items']} items, d={C2['dim']}, "
+                   f"P={C2['num_pos']}, fp32, best of {len(times)}: {best * 1e3:.0f} ms; rate scaled by N_s/N"),
+        "ms_sample": best * 1e3,
+    }
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 5)
+    base = cpu_reference_rate(steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": base["value"],
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": min(args.warmup, 1),
+        "ms_per_step": base["ms_sample"] * C2["num_items"] / 8192,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2 MovieLens-32M-shaped: 4096 x 87585, d=128, P=32, sampled-softmax (InfoNCE) fwd+bwd",
+                   "note": "CPU port of xfmr_rec/losses.py (oracle/losses_oracle.py); the Python reference is absent on the GPU box"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))  # noqa: T201
+
+
+def bench_retrieval(device: torch.device, world: int, rank: int, num_items_total: int, num_queries: int, k: int) -> dict:
+    """Exact top-k over a row-sharded catalog (config 5 shape, catalog size reduced by default)."""
+    import torch.distributed as dist  # noqa: PLC0415
+
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    shard = num_items_total // world
+    items = synthetic.make_catalog(shard, 128, seed=100 + rank, device=device, dtype=torch.bfloat16)
+    queries = synthetic.make_catalog(num_queries, 128, seed=7, device=device, dtype=torch.bfloat16)
+
+    def search(qs: torch.Tensor, kk: int) -> tuple[torch.Tensor, torch.Tensor]:
+        return xfmr_b200.topk_search(qs, items, kk, id_base=rank * shard)
+
+    def step() -> None:
+        if world > 1:
+            xfmr_b200.distributed.sharded_topk(search, xfmr_b200.topk_merge, queries, k)
+        else:
+            search(queries, k)
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    e1.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    flops = 2.0 * num_queries * shard * 128
+    pk = peaks()
+    del items
+    return {"metric": "exact_top100_queries_per_s", "value": num_queries / (ms * 1e-3), "unit": "queries/s",
+            "workload": f"{num_queries} queries x {num_items_total} items (sharded {world} ways), d=128 bf16, k={k}",
+            "ms": ms, "tensor_frac_of_burst_peak": flops / (ms * 1e-3) / (pk["bf16_tflops"] * 1e12)}
+
+
+def bench_gather(device: torch.device) -> dict:
+    import xfmr_b200  # noqa: PLC0415
+
+    n, d, log2 = 1 << 22, 128, 22
+    gen = torch.Generator(device=device).manual_seed(3)
+    table = (torch.randn(1 << log2, d, device=device, generator=gen) * 0.02).to(torch.bfloat16)
+    ids = torch.randint(0, 2**62, (n,), device=device, generator=gen)
+    fn = lambda: xfmr_b200.hash_embedding_gather(table, ids, 2)  # noqa: E731
+    times = timed_steps(fn, 10, 3, None)
+    ms = statistics.median(times)
+    algo_bytes = n * (8 + 2 * d * 2 + d * 2)
+    pk = peaks()
+    return {"metric": "hash_gather_GBps", "value": algo_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ms,
+            "workload": "C4: 4Mi ids, k=2 hashes, 2^22 x 128 bf16 table", "frac_of_hbm_peak": algo_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+
+
+def main() -> None:  # noqa: PLR0915
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (skip per-loss / retrieval / gather / cpu baseline)")
+    ap.add_argument("--retrieval-items", type=int, default=8_000_000, help="catalog rows of the retrieval extra (config 5 is 100,000,000)")
+    ap.add_argument("--retrieval-queries", type=int, default=65_536)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist  # noqa: PLC0415
+
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200 import _lib  # noqa: PLC0415
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    inp = make_c2(device, rank, torch.bfloat16)
+    module = getattr(xfmr_b200, HEADLINE_LOSS)(sigma=SIGMA, margin=MARGIN)
+    step = loss_step_fn(module, inp)
+    flush_buf = torch.zeros(64 << 20, dtype=torch.float32, device=device)
+
+    # ---- device-resident timing (value) + live sweep-kernel timing (roofline)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(warmup):
+        flush_l2(flush_buf)
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.launch_count(reset=True)
+    _lib.sweep_timing(True)
+    clocks.mark_begin()
+    times = timed_steps(step, args.steps, 0, flush_buf)
+    torch.cuda.synchronize()
+    clocks.mark_end()
+    clocks.stop()
+    sweep_ms_total, sweep_count = _lib.sweep_timing_read()
+    _lib.sweep_timing(False)
+    launches = _lib.launch_count()
+    total_ms = torch.tensor([sum(times)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * C2["batch"] / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with host (pinned) inputs
+    host = {k: v.cpu().pin_memory() for k, v in inp.items() if k != "log_q"}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step() -> float:
+        dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        q = dev["user_embed"].requires_grad_(True)
+        v = dev["item_embed"].requires_grad_(True)
+        loss = module(q, v, dev["target"], item_idx=dev["item_idx"], pos_idx=dev["pos_idx"])
+        loss.backward()
+        return float(loss)  # device -> host read of the step's result (synchronises)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(5, min(args.steps, 20))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * C2["batch"] * e2e_steps / float(e2e_s)
+
+    pk = peaks()
+    algo_flops = 6.0 * C2["batch"] * C2["num_items"] * C2["dim"]  # fwd 2BNd + dQ 2BNd + dI 2BNd
+    sweep_ms_per_step = sweep_ms_total / args.steps
+    achieved = algo_flops / (sweep_ms_per_step * 1e-3) / 1e12
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": "C2 MovieLens-32M-shaped: batch 4096 x 87585 items, d=128, P=32, bf16, sampled-softmax "
+                        "(InfomationNoiseContrastiveEstimationLoss) fwd+bwd through the drop-in module",
+            "sigma": SIGMA, "margin": MARGIN, "num_negatives": 0,
+            "l2": "flushed between steps (256 MiB read+write)",
+            "parallelism": f"dp{world} (users sharded, no data-path collective)",
+        },
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {
+            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "kernel": "xb::sweep_kernel (3 launches per step: loss statistics, dQ, dI)",
+            "algorithmic_flops_per_step": algo_flops, "sweep_ms_per_step": sweep_ms_per_step,
+            "sweep_launches_per_step": sweep_count / args.steps, "peak_source": pk["source"] + " sustained bf16",
+            "sweep_share_of_step": sweep_ms_per_step / ms_per_step,
+        },
+    }
+
+    if not args.no_extras:
+        per_loss = {}
+        for name in xfmr_b200.LOSS_SLOTS:
+            m = getattr(xfmr_b200, name)(sigma=SIGMA, margin=MARGIN)
+            t = timed_steps(loss_step_fn(m, inp), 8, 3, flush_buf)
+            per_loss[name] = {"ms_per_step": statistics.median(t), "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
+        mined = xfmr_b200.PairwiseHingeLoss(num_negatives=4, sigma=SIGMA, margin=MARGIN)  # the reference's training default
+        t = timed_steps(loss_step_fn(mined, inp), 8, 3, flush_buf)
+        per_loss["PairwiseHingeLoss[num_negatives=4]"] = {"ms_per_step": statistics.median(t),
+                                                           "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
+
+        def fused_fwd() -> None:
+            xfmr_b200.fused_losses(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"],
+                                   pos_idx=inp["pos_idx"], sigma=SIGMA, margin=MARGIN)
+
+        t = timed_steps(fused_fwd, 8, 3, flush_buf)
+        per_loss["all_seven_forward_one_call"] = {"ms_per_step": statistics.median(t)}
+        line["per_loss"] = per_loss
+        del inp, host
+        torch.cuda.empty_cache()
+        line["retrieval"] = bench_retrieval(device, world, rank, args.retrieval_items, args.retrieval_queries, 100)
+        if rank == 0:
+            line["gather"] = bench_gather(device)
+            base = cpu_reference_rate(2, 1)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    elif rank == 0:
+        base = cpu_reference_rate(1, 1)
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        print(json.dumps(line))  # noqa: T201
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

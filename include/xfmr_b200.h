@@ -161,9 +161,22 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
                     const void* rows, const void* cols, float* s_out, float* acc_out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Measurement hook (bench.py only): while enabled, every tensor-core sweep launch is
+ * bracketed by CUDA events on its stream.  xb_sweep_timing(1) starts (and clears), xb_sweep_timing(0) stops;
+ * xb_sweep_timing_read synchronises on the recorded events (the one entry point that blocks the host) and
+ * returns the summed device time in milliseconds and the number of sweep launches. */
+int xb_sweep_timing(int32_t enable);
+int xb_sweep_timing_read(double* total_ms_host, int64_t* count_host);
+
+/* Test hook: where a named region of the loss workspace lives (valid after xb_loss_forward).
+ * region 0 = mined columns int32 [B][K] (-1 = none), 1 = their logits (log2 units) fp32 [B][K],
+ * 2 = pair mask uint32 [B_pad][xb_mask_words(N)], 3 = row statistics float4 [B] {count, lse, lse+pos, 1/count},
+ * 4 = mining candidates uint64 [B][2*(K+16)]. */
+int xb_debug_loss_region(const xb_loss_desc* desc, int32_t region, size_t* offset_host, size_t* bytes_host);
+
 const char* xb_last_error_string(void);
 const char* xb_version(void);
-/* number of kernel launches issued through this library on the calling thread since the last reset */
+/* number of kernel launches issued through this library (process-wide) since the last reset */
 int64_t xb_launch_count(int32_t reset);
 
 #ifdef __cplusplus

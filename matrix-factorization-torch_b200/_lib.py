@@ -88,6 +88,9 @@ SIGNATURES = {
     "xb_hash_scatter_grad": (_i32, [_vp, _i64, _i32, _u32, _vp, _i32, _i32, _vp, _vp]),
     "xb_debug_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "xb_debug_scores": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xb_debug_loss_region": (_i32, [ctypes.POINTER(LossDesc), _i32, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "xb_sweep_timing": (_i32, [_i32]),
+    "xb_sweep_timing_read": (_i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "xb_last_error_string": (ctypes.c_char_p, []),
     "xb_version": (ctypes.c_char_p, []),
     "xb_launch_count": (_i64, [_i32]),
@@ -165,6 +168,19 @@ def compute_code(compute: str | None, dtype: torch.dtype) -> int:
         return XB_COMPUTE_SPLIT
     msg = f"compute must be None, 'bf16' or 'fp32', got {compute!r}"
     raise ValueError(msg)
+
+
+def sweep_timing(enable: bool) -> None:  # noqa: FBT001
+    """Measurement hook: bracket every sweep launch with CUDA events (see ``xb_sweep_timing``)."""
+    check(lib.xb_sweep_timing(1 if enable else 0), "xb_sweep_timing")
+
+
+def sweep_timing_read() -> tuple[float, int]:
+    """``(total sweep milliseconds, number of sweep launches)`` since ``sweep_timing(True)``; blocks the host."""
+    total = ctypes.c_double(0.0)
+    count = ctypes.c_int64(0)
+    check(lib.xb_sweep_timing_read(ctypes.byref(total), ctypes.byref(count)), "xb_sweep_timing_read")
+    return total.value, count.value
 
 
 def launch_count(*, reset: bool = False) -> int:

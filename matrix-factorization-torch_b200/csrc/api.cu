@@ -5,11 +5,14 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/xfmr_b200.h"
 #include "aux_kernels.cuh"
@@ -21,7 +24,8 @@ constexpr int NUM_SMS = 148;                // B200; the launch plan (and so the
 constexpr size_t SMEM_BUDGET = 232448;      // 227 KB opt-in dynamic shared memory per CTA
 
 thread_local std::string g_last_error = "";
-thread_local long long g_launches = 0;
+// process-wide (autograd runs the backward on its own thread)
+static std::atomic<long long> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -44,6 +48,29 @@ static int fail(int code, const char* fmt, ...) {
     ++g_launches;                                                                                  \
     cudaError_t _e = cudaGetLastError();                                                           \
     if (_e != cudaSuccess) return fail(XB_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+// Optional measurement hook (bench.py): CUDA events around every sweep launch, on the launch stream.
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timing_mutex;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+
+#define XB_SWEEP(expr)                                                                             \
+  do {                                                                                             \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                                                      \
+    const bool _timed = g_timing.load();                                                           \
+    if (_timed) {                                                                                  \
+      XB_CUDA(cudaEventCreate(&_e0));                                                              \
+      XB_CUDA(cudaEventCreate(&_e1));                                                              \
+      XB_CUDA(cudaEventRecord(_e0, st));                                                           \
+    }                                                                                              \
+    XB_CUDA(expr);                                                                                 \
+    ++g_launches;                                                                                  \
+    if (_timed) {                                                                                  \
+      XB_CUDA(cudaEventRecord(_e1, st));                                                           \
+      std::lock_guard<std::mutex> _lk(g_timing_mutex);                                             \
+      g_timing_events.emplace_back(_e0, _e1);                                                      \
+    }                                                                                              \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
@@ -192,7 +219,7 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
 // ------------------------------------------------------------------------------------------------
 constexpr int MINE_CAP = 256;    // candidate buffer per row for the mining sweep
 constexpr int MINE_KMAX = 64;    // largest supported num_negatives
-constexpr int MINE_OVERFETCH = 32;  // extra candidates re-scored exactly before the final selection (<= 96 total)
+constexpr int MINE_OVERFETCH = 16;  // extra candidates per side re-scored exactly before the final selection
 
 struct LossWs {
   int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
@@ -251,7 +278,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   if (w->mining) {
     w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad * MINE_CAP);
     w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
-    w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * w->Kf);
+    w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w->Kf);
     w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
     w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
   } else {
@@ -347,9 +374,8 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       p.mask_words = w.words;
       p.out_acc = accq;
       p.out_stats = rsq;
-      XB_CUDA(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
+      XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
                                      w.gq.smem, st));
-      ++g_launches;
       nq = w.gq.nchunks;
     }
     {  // dI sweep: rows = items, columns = queries (transposed mask)
@@ -360,9 +386,8 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       p.mask_words = w.words_t;
       p.out_acc = acci;
       p.out_stats = rsi;
-      XB_CUDA(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
+      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
-      ++g_launches;
       ni = w.gi.nchunks;
     }
   }
@@ -384,10 +409,36 @@ extern "C" {
 #pragma GCC visibility push(default)
 
 const char* xb_last_error_string(void) { return g_last_error.c_str(); }
+
+int xb_sweep_timing(int32_t enable) {
+  std::lock_guard<std::mutex> lk(g_timing_mutex);
+  for (auto& ev : g_timing_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_timing_events.clear();
+  g_timing = enable != 0;
+  return XB_OK;
+}
+
+int xb_sweep_timing_read(double* total_ms_host, int64_t* count_host) {
+  if (!total_ms_host || !count_host) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  double total = 0.0;
+  std::lock_guard<std::mutex> lk(g_timing_mutex);
+  for (auto& ev : g_timing_events) {
+    float ms = 0.f;
+    XB_CUDA(cudaEventSynchronize(ev.second));
+    XB_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+  }
+  *total_ms_host = total;
+  *count_host = static_cast<int64_t>(g_timing_events.size());
+  return XB_OK;
+}
 const char* xb_version(void) { return "xfmr_b200 0.1 (sm_100a)"; }
 int64_t xb_launch_count(int32_t reset) {
-  const long long v = g_launches;
-  if (reset) g_launches = 0;
+  const long long v = g_launches.load();
+  if (reset) g_launches.store(0);
   return v;
 }
 int32_t xb_mask_words(int32_t num_items) { return mask_words_for(num_items); }
@@ -398,6 +449,24 @@ size_t xb_loss_workspace_bytes(const xb_loss_desc* desc) {
   LossWs w;
   loss_ws_layout(desc, &w);
   return w.total;
+}
+
+int xb_debug_loss_region(const xb_loss_desc* desc, int32_t region, size_t* offset_host, size_t* bytes_host) {
+  int rc = check_loss_desc(desc);
+  if (rc != XB_OK) return rc;
+  if (!offset_host || !bytes_host) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  LossWs w;
+  loss_ws_layout(desc, &w);
+  const size_t B = desc->batch;
+  switch (region) {
+    case 0: *offset_host = w.selcol; *bytes_host = w.mining ? sizeof(int) * B * w.K : 0; break;
+    case 1: *offset_host = w.selL2; *bytes_host = w.mining ? sizeof(float) * B * w.K : 0; break;
+    case 2: *offset_host = w.mask; *bytes_host = sizeof(uint32_t) * w.B_pad * static_cast<size_t>(w.words); break;
+    case 3: *offset_host = w.rowstat; *bytes_host = sizeof(float4) * B; break;
+    case 4: *offset_host = w.sel; *bytes_host = w.mining ? sizeof(unsigned long long) * B * 2 * w.Kf : 0; break;
+    default: return fail(XB_ERR_INVALID_ARG, "unknown region %d", region);
+  }
+  return XB_OK;
 }
 
 int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void* item_embed, const float* target,
@@ -458,8 +527,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
     if (!w.mining) {
       p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
       p.out_stats = reinterpret_cast<float*>(ws + w.part);
-      XB_CUDA(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
-      ++g_launches;
+      XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
       loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks, p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
                                                      reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
@@ -472,17 +540,18 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
       p.cap = MINE_CAP;
       p.keep = w.Kf;
-      p.topk_mining = 1;
-      XB_CUDA(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
-      ++g_launches;
-      cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
-          B, p.nR_pad, w.fwd.nchunks, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
-          reinterpret_cast<unsigned long long*>(ws + w.sel));
-      XB_LAUNCHED();
+      for (int side = 0; side < 2; ++side) {
+        p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
+        XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
+        cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
+            B, p.nR_pad, w.fwd.nchunks, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
+            reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
+        XB_LAUNCHED();
+      }
       // exact re-score from the original inputs when they carry more precision than the operands
       const bool use_orig = (desc->in_dtype == XB_DTYPE_F32 && desc->compute == XB_COMPUTE_SPLIT);
       mined_forward_kernel<float><<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
-          B, w.K, w.Kf, d, w.kp, w.parts, reinterpret_cast<unsigned long long*>(ws + w.sel),
+          B, w.K, 2 * w.Kf, d, w.kp, w.parts, reinterpret_cast<unsigned long long*>(ws + w.sel),
           use_orig ? static_cast<const float*>(user_embed) : nullptr,
           use_orig ? static_cast<const float*>(item_embed) : nullptr,
           reinterpret_cast<__nv_bfloat16*>(ws + w.qprep), reinterpret_cast<__nv_bfloat16*>(ws + w.iprep),
@@ -635,11 +704,10 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   p.cap = w.cap;
   p.keep = w.kfetch;
   p.topk_mining = 0;
-  XB_CUDA(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
-  ++g_launches;
+  XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
-  cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(Q, p.nR_pad, w.plan.nchunks, w.cap,
-                                                                                 w.kfetch, p.cand, p.cand_cnt, ent);
+  cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(
+      Q, p.nR_pad, w.plan.nchunks, w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
   XB_LAUNCHED();
   float* stmp = reinterpret_cast<float*>(ws + w.scores);
   long long* itmp = reinterpret_cast<long long*>(ws + w.ids);
@@ -780,8 +848,7 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
   p.dbg_s = s_out;
   p.out_acc = acc_out;
   p.out_stats = reinterpret_cast<float*>(ws + w.rs);
-  XB_CUDA(launch_sweep_debug(tmR, tmC, p, dim3(1, w.plan.n_rblocks), w.plan.smem, st));
-  ++g_launches;
+  XB_SWEEP(launch_sweep_debug(tmR, tmC, p, dim3(1, w.plan.n_rblocks), w.plan.smem, st));
   return XB_OK;
 }
 

@@ -384,7 +384,8 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
 // ------------------------------------------------------------------------------------------------
 __global__ void cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap, int k,
                                      const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt,
-                                     unsigned long long* __restrict__ out /*[nrows][k]*/) {
+                                     unsigned long long* __restrict__ out /*[nrows][out_stride], written at out_off*/,
+                                     int out_stride, int out_off) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -411,7 +412,7 @@ __global__ void cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int idx = i * 32 + lane;
-    if (idx < k) out[static_cast<size_t>(row) * k + idx] = best[i];
+    if (idx < k) out[static_cast<size_t>(row) * out_stride + out_off + idx] = best[i];
   }
 }
 
@@ -508,10 +509,14 @@ __global__ void fill_topk_empty_kernel(size_t n, float* __restrict__ scores, lon
 // top-K selection.  So the sweep over-fetches Kf > K candidates per row and this kernel re-scores them
 // in fp32 from the original inputs, applies the reference's order exactly
 //   key = bits(R) ^ 0x7fffffff,  R = L_ij - L_ii   (semi-hard R<0 by R descending, then hard by R ascending)
-// and keeps the best K.  One warp per query row; Kf <= 96 (three candidates per lane).
+// and keeps the best K.  The order is discontinuous at R = 0 (a barely negative R ranks first, a barely
+// positive one after every semi-hard column), so the candidates come from TWO sweeps — the reference
+// order and its mirror image — which together hold the columns closest to R = 0 on both sides no matter
+// how rounding placed them; duplicates between the two lists are dropped here.
+// One warp per query row; Kc = 2 * Kf <= 160 candidates (five per lane).
 //   selcol[i][r] = chosen column of rank r (or -1), selL2[i][r] = its logit in log2 units.
 // ------------------------------------------------------------------------------------------------
-constexpr int MINE_SLOTS = 3;
+constexpr int MINE_SLOTS = 5;
 
 template <typename T>
 __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int parts,
@@ -526,50 +531,75 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   const float4 qf = qfwd[row];
-  const float l2ii = rowinfo[row].w;
-  uint32_t key_[MINE_SLOTS];
+  unsigned long long key_[MINE_SLOTS];
   int col_[MINE_SLOTS];
   float l2_[MINE_SLOTS];
 #pragma unroll
-  for (int t = 0; t < MINE_SLOTS; ++t) { key_[t] = 0u; col_[t] = -1; l2_[t] = 0.f; }
-  // phase 1: exact logits of the candidates
+  for (int t = 0; t < MINE_SLOTS; ++t) { key_[t] = 0ull; col_[t] = -1; l2_[t] = 0.f; }
+  // phase 1: exact logits of the candidates.  R = L_ij - L_ii decides semi-hard vs hard by its SIGN, so it
+  // is evaluated in fp64 in the reference's own form (half squared distances, losses.py:9-12, :144):
+  //   R = a * (D_ii - D_ij) - (lq_j - lq_i)
+  const bool use_orig = orig_q != nullptr;
+  const int dlen = use_orig ? d : kp;
+  auto qval = [&](int kk) -> double {
+    return use_orig ? static_cast<double>(static_cast<float>(orig_q[static_cast<size_t>(row) * d + kk]))
+                    : static_cast<double>(prepped_val(qp + static_cast<size_t>(row) * parts * kp, kp, parts, kk));
+  };
+  auto ival = [&](int r, int kk) -> double {
+    return use_orig ? static_cast<double>(static_cast<float>(orig_i[static_cast<size_t>(r) * d + kk]))
+                    : static_cast<double>(prepped_val(ip + static_cast<size_t>(r) * parts * kp, kp, parts, kk));
+  };
+  auto half_sq_dist = [&](int r) -> double {
+    double acc = 0.0;
+    for (int kk = lane; kk < dlen; kk += 32) {
+      const double df = qval(kk) - ival(r, kk);
+      acc = fma(df, df, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return 0.5 * acc;
+  };
+  const double a2d = static_cast<double>(qf.x);
+  const double dii = half_sq_dist(row);
+  const double lq2i = static_cast<double>(ipar[row].y);
   for (int s = 0; s < Kf; ++s) {
     const unsigned long long e = cand_sel[static_cast<size_t>(row) * Kf + s];
     if (e == 0ull) continue;  // warp-uniform
     const int col = static_cast<int>(~static_cast<uint32_t>(e & 0xffffffffull));
-    float acc = 0.f;
-    if (orig_q != nullptr) {
-      const T* q = orig_q + static_cast<size_t>(row) * d;
-      const T* v = orig_i + static_cast<size_t>(col) * d;
-      for (int kk = lane; kk < d; kk += 32) acc = fmaf(static_cast<float>(q[kk]), static_cast<float>(v[kk]), acc);
-    } else {
-      const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
-      const __nv_bfloat16* v = ip + static_cast<size_t>(col) * parts * kp;
-      for (int kk = lane; kk < kp; kk += 32)
-        acc = fmaf(prepped_val(q, kp, parts, kk), prepped_val(v, kp, parts, kk), acc);
-    }
-    acc = warp_sum(acc);
-    const float2 ipj = ipar[col];
-    const float l2 = fmaf(qf.x, acc + ipj.x, qf.y) - ipj.y;
-    const float r = (l2 - l2ii) + 0.0f;
-    uint32_t key = __float_as_uint(r) ^ 0x7fffffffu;
-    key = (r != r) ? 1u : max(key, 1u);
+    const double dij = half_sq_dist(col);
+    const double lq2j = static_cast<double>(ipar[col].y);
+    double r = a2d * (dii - dij) - (lq2j - lq2i);
+    r += 0.0;  // -0 -> +0 (hard side, losses.py:149 tests `< 0`)
+    unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(r)) ^ 0x7fffffffffffffffull;
+    key = (r != r) ? 1ull : (key < 1ull ? 1ull : key);
+    const float l2 = static_cast<float>(-a2d * dij - lq2j);
     if ((s & 31) == lane) {
 #pragma unroll
       for (int t = 0; t < MINE_SLOTS; ++t)
         if ((s >> 5) == t) { key_[t] = key; col_[t] = col; l2_[t] = l2; }
     }
   }
-  // phase 2: rank = number of candidates ordered before this one (key desc, column asc)
+  // phase 2a: drop the later copy of a column that both candidate lists delivered
+#pragma unroll
+  for (int tt = 0; tt < MINE_SLOTS; ++tt) {
+    for (int src = 0; src < 32; ++src) {
+      const int oc = __shfl_sync(0xffffffffu, col_[tt], src);
+      if (oc < 0) continue;  // warp-uniform
+#pragma unroll
+      for (int t = 0; t < MINE_SLOTS; ++t)
+        if (oc == col_[t] && tt * 32 + src < t * 32 + lane) key_[t] = 0ull;
+    }
+  }
+  // phase 2b: rank = number of candidates ordered before this one (key desc, column asc)
   int rank_[MINE_SLOTS];
 #pragma unroll
   for (int t = 0; t < MINE_SLOTS; ++t) rank_[t] = 0;
 #pragma unroll
   for (int tt = 0; tt < MINE_SLOTS; ++tt) {
     for (int src = 0; src < 32; ++src) {
-      const uint32_t ok = __shfl_sync(0xffffffffu, key_[tt], src);
+      const unsigned long long ok = __shfl_sync(0xffffffffu, key_[tt], src);
       const int oc = __shfl_sync(0xffffffffu, col_[tt], src);
-      if (ok == 0u) continue;  // warp-uniform
+      if (ok == 0ull) continue;  // warp-uniform
 #pragma unroll
       for (int t = 0; t < MINE_SLOTS; ++t)
         rank_[t] += (ok > key_[t] || (ok == key_[t] && oc < col_[t])) ? 1 : 0;
@@ -581,7 +611,7 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
   float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG;
 #pragma unroll
   for (int t = 0; t < MINE_SLOTS; ++t) {
-    const bool keep = key_[t] != 0u && rank_[t] < K;
+    const bool keep = key_[t] != 0ull && rank_[t] < K;
     if (keep) {
       selcol[static_cast<size_t>(row) * K + rank_[t]] = col_[t];
       selL2[static_cast<size_t>(row) * K + rank_[t]] = l2_[t];
@@ -593,7 +623,7 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
       lsum += x > 40.f ? x : log2f(1.f + exp2f(x));
       mx = fmaxf(mx, l2);
     } else {
-      key_[t] = 0u;
+      key_[t] = 0ull;
     }
   }
 #pragma unroll
@@ -601,7 +631,7 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
   float se = 0.f;
 #pragma unroll
   for (int t = 0; t < MINE_SLOTS; ++t)
-    if (key_[t] != 0u) se += exp2f(l2_[t] - mx);
+    if (key_[t] != 0ull) se += exp2f(l2_[t] - mx);
   cnt = warp_sum(cnt); csum = warp_sum(csum); hsum = warp_sum(hsum); lsum = warp_sum(lsum); se = warp_sum(se);
   if (lane == 0) {
     const float lseM2 = se > 0.f ? mx + log2f(se) : -INFINITY;

@@ -68,7 +68,8 @@ struct SweepParams {
   int* cand_cnt;             // [nchunks][nR_pad]
   int cap;                   // candidate buffer capacity per row (power of two, 64..1024)
   int keep;                  // entries kept by a compaction (<= cap/2)
-  int topk_mining;           // 0: key = order(S)   1: key = bits(L2 - L2_ii) ^ 0x7fffffff (semi-hard order)
+  int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
+                             // 2: same with R negated (hard side first)
 };
 
 struct SweepSmemLayout {
@@ -555,7 +556,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               const float2 ip = *reinterpret_cast<const float2*>(cpar_s + (ch * 32 + c) * 2);
               float l2 = fmaf(rp_reg[0], S + ip.x, rp_reg[1]);
               if (LOGQ) l2 -= ip.y;
-              const float r = (l2 + rp_reg[2]) + 0.0f;       // rp_reg[2] = -L2_ii: R = L_ij - L_ii; -0 -> +0
+              float r = l2 + rp_reg[2];                        // rp_reg[2] = -L2_ii: R = L_ij - L_ii
+              if (p.topk_mining == 2) {
+                r = (r == 0.f) ? -0.0f : -r;                   // mirrored order; an exact 0 belongs to BOTH first groups
+              } else {
+                r += 0.0f;                                     // -0 -> +0 (losses.py:149 tests `< 0`)
+              }
               k = __float_as_uint(r) ^ 0x7fffffffu;           // semi-hard (R<0, desc) before hard (R>=0, asc)
               k = (r != r) ? 1u : max(k, 1u);
             } else {

@@ -1,0 +1,91 @@
+"""Host-side behaviour that needs no GPU: argument checking with the reference's error behaviour
+(xfmr_rec/losses.py:54-79), loud failure instead of a CPU fallback, the class surface, fake-tensor shapes."""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+import xfmr_b200
+from xfmr_b200 import synthetic
+
+
+def test_same_seven_class_names_and_constructor_keywords() -> None:
+    names = [
+        "AlignmentLoss", "ContrastiveLoss", "AlignmentContrastiveLoss", "InfomationNoiseContrastiveEstimationLoss",
+        "MutualInformationNeuralEstimationLoss", "PairwiseHingeLoss", "PairwiseLogisticLoss",
+    ]
+    for n in names:
+        module = getattr(xfmr_b200, n)(num_negatives=4, sigma=2.0, margin=0.5)   # lightning.py:279-286
+        assert isinstance(module, torch.nn.Module)
+        assert (module.num_negatives, module.sigma, module.margin) == (4, 2.0, 0.5)
+        assert type(module).__name__ == n                                       # selected by class name, lightning.py:139
+    torch.nn.ModuleList([c() for c in xfmr_b200.LOSS_CLASSES])                  # lightning.py:270-278
+
+
+@pytest.mark.parametrize(("q", "v", "t"), [
+    (torch.zeros(4, 8, 2), torch.zeros(6, 8), torch.zeros(4)),     # rank != 2
+    (torch.zeros(4, 8), torch.zeros(8), torch.zeros(4)),
+    (torch.zeros(4, 8), torch.zeros(6, 9), torch.zeros(4)),         # width mismatch
+    (torch.zeros(4, 8), torch.zeros(6, 8), torch.zeros(5)),         # target rows != user rows
+    (torch.zeros(4, 8), torch.zeros(3, 8), torch.zeros(4)),         # fewer items than users
+])
+def test_shape_errors_are_value_errors(q: torch.Tensor, v: torch.Tensor, t: torch.Tensor) -> None:
+    loss = xfmr_b200.PairwiseHingeLoss()
+    with pytest.raises(ValueError):  # noqa: PT011
+        loss(q, v, t, item_idx=torch.arange(v.size(0)), pos_idx=torch.zeros(4, 1, dtype=torch.int64))
+
+
+def test_cpu_tensors_fail_loudly() -> None:
+    inp = synthetic.make_loss_inputs(8, 16, 8, 2, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.InfomationNoiseContrastiveEstimationLoss()(inp["user_embed"], inp["item_embed"], inp["target"],
+                                                              item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.topk_search(inp["user_embed"], inp["item_embed"], 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.hash_indices(torch.arange(4), 2, 10)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.hash_embedding_gather(torch.zeros(16, 8, dtype=torch.bfloat16), torch.arange(4), 2)
+
+
+def test_fake_tensor_shapes() -> None:
+    """register_fake: shape inference without touching the GPU (torch.compile / export tracing)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode  # noqa: PLC0415
+
+    with FakeTensorMode():
+        q = torch.empty(64, 32, device="cuda")
+        v = torch.empty(200, 32, device="cuda")
+        t = torch.empty(64, device="cuda")
+        idx = torch.empty(200, dtype=torch.int64, device="cuda")
+        pos = torch.empty(64, 4, dtype=torch.int64, device="cuda")
+        losses, ws = torch.ops.xfmr_b200.loss_fwd(q, v, t, idx, pos, None, 0, 1.0, 1.0, 127, 1)
+        assert losses.shape == (7,) and losses.dtype == torch.float32
+        assert ws.dtype == torch.uint8 and ws.numel() > 0
+        dq, dv = torch.ops.xfmr_b200.loss_bwd(ws, losses, 64, 200, 32, 4, False, False, 0, 1.0, 1.0, 127, 1)
+        assert dq.shape == (64, 32) and dv.shape == (200, 32)
+
+
+def test_unsupported_shapes_are_reported_by_the_library() -> None:
+    import ctypes  # noqa: PLC0415
+
+    from xfmr_b200 import _lib  # noqa: PLC0415
+
+    wide = _lib.TopkDesc(num_queries=4, num_items=100, dim=300, k=10, in_dtype=0, compute=0, has_exclusions=0, reserved=0, id_base=0)
+    assert _lib.lib.xb_topk_workspace_bytes(ctypes.byref(wide)) == 0
+    assert b"dim" in _lib.lib.xb_last_error_string()
+    big_k = _lib.TopkDesc(num_queries=4, num_items=100, dim=64, k=1000, in_dtype=0, compute=0, has_exclusions=0, reserved=0, id_base=0)
+    assert _lib.lib.xb_topk_workspace_bytes(ctypes.byref(big_k)) == 0
+    mined = _lib.LossDesc(batch=8, num_items=1000, dim=64, num_pos=0, in_dtype=0, compute=1, num_negatives=100,
+                          loss_mask=8, sigma=1.0, margin=1.0, has_log_q=0, reserved=0)
+    assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(mined)) == 0
+
+
+def test_synthetic_inputs_follow_the_reference_layout() -> None:
+    inp = synthetic.make_loss_inputs(64, 200, 16, 8, n_catalog=500, seed=1)
+    assert inp["item_idx"].min() >= 1                       # 0 is reserved for padding (data/prepare.py:85)
+    assert (inp["pos_idx"][:, 0] == inp["item_idx"][:64]).all()
+    assert inp["pos_idx"].dtype == torch.int64 and (inp["pos_idx"] >= 0).all()
+    assert torch.allclose(inp["user_embed"].norm(dim=-1), torch.ones(64), atol=1e-5)   # models.py:59
+    assert set(inp["target"].tolist()) <= {1.0, 2.0, 3.0, 4.0, 5.0}                    # ratings, params.py:8
+    assert inp["item_idx"][64:].unique().numel() == 136                                  # negatives without replacement
