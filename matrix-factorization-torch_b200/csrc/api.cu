@@ -264,20 +264,20 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->mask = take(sizeof(uint32_t) * w->B_pad * static_cast<size_t>(w->words));
   w->mask_t = take(sizeof(uint32_t) * w->N_pad * static_cast<size_t>(w->words_t));
   w->pm_ws = take(pair_mask_ws(N).total);
-  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
+  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad);
   w->rowstat = take(sizeof(float4) * B);
   w->rowloss = take(sizeof(float) * 7 * B);
   w->ueff = take(sizeof(float) * 8);
   w->qg = take(sizeof(float) * 12 * B);
   const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
   w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
-  w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * w->B_pad);
+  w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * EPI_HALVES * w->B_pad);
   w->acci = take(sizeof(float) * static_cast<size_t>(ni) * w->N_pad * w->kp);
-  w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * w->N_pad);
+  w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * EPI_HALVES * w->N_pad);
   w->gdiag = take(sizeof(float) * B);
   if (w->mining) {
-    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad * MINE_CAP);
-    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
+    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad * MINE_CAP);
+    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad);
     w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w->Kf);
     w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
     w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
@@ -347,7 +347,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   float* acci = reinterpret_cast<float*>(ws + w.acci);
   float* rsi = reinterpret_cast<float*>(ws + w.rsi);
   float* gdiag = reinterpret_cast<float*>(ws + w.gdiag);
-  int nq = 1, ni = 1;
+  int nq = 1, ni = 1, nq_sub = 1, ni_sub = 1;
   if (lm == 0 || w.mining) {
     XB_CUDA(cudaMemsetAsync(accq, 0, sizeof(float) * static_cast<size_t>(w.B_pad) * w.kp, st));
     XB_CUDA(cudaMemsetAsync(rsq, 0, sizeof(float) * 2 * static_cast<size_t>(w.B_pad), st));
@@ -377,6 +377,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
                                      w.gq.smem, st));
       nq = w.gq.nchunks;
+      nq_sub = nq * EPI_HALVES;
     }
     {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
@@ -389,14 +390,15 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
+      ni_sub = ni * EPI_HALVES;
     }
   }
   grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
-      B, d, w.kp, w.parts, w.B_pad, nq, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
+      B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
       dq, gdiag);
   XB_LAUNCHED();
   grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(N) * 32, 256), 256, 0, st>>>(
-      N, B, d, w.kp, w.parts, w.N_pad, ni, acci, rsi, iprep, qprep, gdiag, di);
+      N, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
   XB_LAUNCHED();
   return XB_OK;
 }
@@ -528,7 +530,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
       p.out_stats = reinterpret_cast<float*>(ws + w.part);
       XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
-      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks, p.out_stats, desc->sigma,
+      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * EPI_HALVES, p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
                                                      reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
       XB_LAUNCHED();
@@ -544,7 +546,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
-            B, p.nR_pad, w.fwd.nchunks, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
+            B, p.nR_pad, w.fwd.nchunks * EPI_HALVES, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
         XB_LAUNCHED();
       }
@@ -639,8 +641,8 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->qprep = take(rowb * d->num_queries);
   w->iprep = take(w->items_inplace ? 0 : rowb * static_cast<size_t>(d->num_items));
-  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * w->Q_pad * w->cap);
-  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * w->Q_pad);
+  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * EPI_HALVES * w->Q_pad * w->cap);
+  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * EPI_HALVES * w->Q_pad);
   w->ent = take(sizeof(unsigned long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->scores = take(sizeof(float) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->ids = take(sizeof(long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
@@ -707,7 +709,7 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
   cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(
-      Q, p.nR_pad, w.plan.nchunks, w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
+      Q, p.nR_pad, w.plan.nchunks * EPI_HALVES, w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
   XB_LAUNCHED();
   float* stmp = reinterpret_cast<float*>(ws + w.scores);
   long long* itmp = reinterpret_cast<long long*>(ws + w.ids);
@@ -810,7 +812,7 @@ bool debug_ws_layout(int nR, int nC, int dim, int compute, DebugWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->rprep = off; off = align_up(off + rowb * nR, 256);
   w->cprep = off; off = align_up(off + rowb * nC, 256);
-  w->rs = off; off = align_up(off + sizeof(float) * 2 * cdiv(nR, BM) * BM, 256);
+  w->rs = off; off = align_up(off + sizeof(float) * 2 * EPI_HALVES * cdiv(nR, BM) * BM, 256);
   w->total = off;
   return w->plan.ok;
 }

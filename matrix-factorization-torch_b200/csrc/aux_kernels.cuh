@@ -321,7 +321,7 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
 // G_ii = -target*sigma*uA - RGH_i + a*w*(uI*(p_ii - 1) - uM)
 // One warp per query row.  gdiag[i] = G_ii is kept for the item-side finalisation.
 template <typename T>
-__global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_pad, int nchunks,
+__global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_pad, int nchunks, int nsub,
                                        const float* __restrict__ acc, const float* __restrict__ rs_part,
                                        const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ ip,
                                        const float* __restrict__ u, float sigma, uint32_t loss_mask,
@@ -331,7 +331,7 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   float rg = 0.f, rgh = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = 0; c < nsub; ++c) {
     const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);
     rg += r.x;
     rgh += r.y;
@@ -357,7 +357,7 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
 
 // dV_j = sum_i G_ij q_i - CG_j v_j + [j < B] G_jj (q_j - v_j)     (dS/dv = q - v)
 template <typename T>
-__global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, int nR_pad, int nchunks,
+__global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, int nR_pad, int nchunks, int nsub,
                                        const float* __restrict__ acc, const float* __restrict__ rs_part,
                                        const __nv_bfloat16* __restrict__ ip, const __nv_bfloat16* __restrict__ qp,
                                        const float* __restrict__ gdiag, T* __restrict__ di) {
@@ -365,7 +365,7 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   float cg = 0.f;
-  for (int c = 0; c < nchunks; ++c) cg += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
+  for (int c = 0; c < nsub; ++c) cg += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
   const float gjj = row < B ? gdiag[row] : 0.f;
   const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
   const __nv_bfloat16* q = qp + static_cast<size_t>(row < B ? row : 0) * parts * kp;

@@ -13,8 +13,10 @@
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (thread <-> TMEM lane <-> tile row).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue: thread <-> (TMEM lane = tile row, column half).  Two epilogue warps share each SM
+// sub-partition so that one computes while the other waits on tcgen05.ld / MUFU / shared memory.
+// Per-row outputs are written per "sub-chunk" = 2 * column chunk + column half and merged by the finalisers.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -28,8 +30,9 @@ constexpr int BM = 128;                  // tile rows  (UMMA M)
 constexpr int BN = 128;                  // tile cols  (UMMA N of the score MMA)
 constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
 constexpr int BLOCK_BYTES = 128 * 128;   // one [128 rows x 64 bf16] SWIZZLE_128B block
-constexpr int SWEEP_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_HALVES = 2;              // epilogue warps come in two sets; set h owns tile columns [64h, 64h+64)
+constexpr int EPI_THREADS = 128 * EPI_HALVES;
+constexpr int SWEEP_THREADS = 64 + EPI_THREADS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_ACC_COL = 256;   // columns [256, 256+kp) hold the gradient accumulator
 constexpr int MAX_STAGES = 4;
@@ -60,12 +63,12 @@ struct SweepParams {
   const float* cpar;
   const uint32_t* mask; // [nR_pad][mask_words] bit (r, c) set => pair excluded (incl. c >= nC padding)
   int mask_words;       // 32-bit words per mask row = 4 * n_ctiles
-  float* out_stats;     // FWD : [nchunks][nR_pad][8]   GRAD: [nchunks][nR_pad][2] (row sums of G)
+  float* out_stats;     // FWD : [2*nchunks][nR_pad][8]   GRAD: [2*nchunks][nR_pad][2] (row sums of G)
   float* out_acc;       // GRAD: [nchunks][nR_pad][kp] partial accumulators
   float* dbg_s;         // DEBUG: [nR_pad][n_ctiles*BN] raw score tiles
   // TOPK
-  unsigned long long* cand;  // [nchunks][nR_pad][cap] candidate entries (key << 32 | ~col)
-  int* cand_cnt;             // [nchunks][nR_pad]
+  unsigned long long* cand;  // [2*nchunks][nR_pad][cap] candidate entries (key << 32 | ~col)
+  int* cand_cnt;             // [2*nchunks][nR_pad]
   int cap;                   // candidate buffer capacity per row (power of two, 64..1024)
   int keep;                  // entries kept by a compaction (<= cap/2)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
@@ -428,13 +431,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
   } else if (T > 0) {
     // ======================================================================== epilogue warps
-    const int quad = warp & 3;
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;               // column half of the tile this warp reduces
     const int row_l = quad * 32 + lane;             // tile row == TMEM lane
-    const int e_tid = threadIdx.x - 64;             // 0..127, used for cooperative parameter loads
+    const int e_tid = threadIdx.x - 64;             // 0..255, used for cooperative parameter loads
     const int row = rb * BM + row_l;
     const bool row_ok = row < p.nR;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const size_t out_row = static_cast<size_t>(chunk) * p.nR_pad + row;
+    const size_t out_row = static_cast<size_t>(chunk * EPI_HALVES + half) * p.nR_pad + row;
 
     float rp_reg[RPAR];
 #pragma unroll
@@ -458,22 +462,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       float* cpar_s = sPar;
       if (t > 0) named_bar_sync(2, EPI_THREADS);
       if (MODE == MODE_FWD || MODE == MODE_GRAD || (MODE == MODE_TOPK)) {
-        const int j = j0 + e_tid;
+        const int jl = e_tid & (BN - 1);
+        const int j = j0 + jl;
         if (p.cpar != nullptr) {
-#pragma unroll
-          for (int i = 0; i < CPAR; ++i)
-            cpar_s[e_tid * CPAR + i] = (j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
+          for (int i = e_tid >> 7; i < CPAR; i += EPI_HALVES)
+            cpar_s[jl * CPAR + i] = (j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
         }
       }
-      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      uint32_t mw[2] = {0u, 0u};
       if (mrow != nullptr) {
-        const uint4 m4 = *reinterpret_cast<const uint4*>(mrow + (j0 >> 5));
-        mw[0] = m4.x; mw[1] = m4.y; mw[2] = m4.z; mw[3] = m4.w;
+        const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (j0 >> 5) + 2 * half);
+        mw[0] = m2.x; mw[1] = m2.y;
       } else {
         // no mask given: only the column bound applies
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int rem = p.nC - (j0 + 32 * c);
+        for (int c = 0; c < 2; ++c) {
+          const int rem = p.nC - (j0 + 32 * (2 * half + c));
           mw[c] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
         }
       }
@@ -484,11 +488,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if (HAS_G) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
 
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = 2 * half + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(b * BN + ch * 32), v);
         tmem_ld_wait();
-        const uint32_t mwc = mw[ch];
+        const uint32_t mwc = mw[cc];
 
         if (MODE == MODE_FWD) {
           const float4 qp = make_float4(rp_reg[0], rp_reg[1], rp_reg[2], rp_reg[3]);
@@ -618,8 +623,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     if (HAS_G) {
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
-      float* o = p.out_acc + out_row * p.kp;
-      for (int cc = 0; cc < p.kp / 32; ++cc) {
+      float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
+      const int per_half = p.kp / 32 / EPI_HALVES;   // kp is a multiple of 64
+      for (int cc = half * per_half; cc < (half + 1) * per_half; ++cc) {
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + TMEM_ACC_COL + static_cast<uint32_t>(cc * 32), v);
         tmem_ld_wait();

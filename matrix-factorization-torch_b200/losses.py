@@ -190,6 +190,8 @@ def _(workspace, d_losses, batch, num_items, dim, num_pos, bf16_io, has_log_q, n
 def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
     user_embed, item_embed, _target, _item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute = inputs
     _losses, workspace = output
+    ctx.mark_non_differentiable(workspace)
+    ctx.set_materialize_grads(False)  # never allocate a zero "gradient" for the workspace bytes
     ctx.save_for_backward(workspace)
     ctx.meta = (
         user_embed.size(0),
@@ -208,6 +210,8 @@ def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
 
 def _backward(ctx, d_losses, _d_workspace):  # noqa: ANN001, ANN202
     (workspace,) = ctx.saved_tensors
+    if d_losses is None:
+        return (None,) * 11
     d_user, d_item = _loss_bwd(workspace, d_losses.contiguous().float(), *ctx.meta)
     return d_user, d_item, None, None, None, None, None, None, None, None, None
 
