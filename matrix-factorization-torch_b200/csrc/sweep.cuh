@@ -123,12 +123,19 @@ struct FwdState {
 template <int LM, bool LOGQ, bool MASKED>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, const float4 qp,
                                           const float2* __restrict__ colp, FwdState<LM>& st) {
+  constexpr bool LSE = (LM & (LM_INFONCE | LM_MINE)) != 0;
+  constexpr bool OTHER = (LM & ~(LM_INFONCE | LM_MINE)) != 0;
+  // Logits are formed RELATIVE to the running maximum (L - mref) so that the common case needs no
+  // subtraction before exp2; `mref` is 0 until the row has seen a finite logit.
+  const bool fresh = st.mx == NEG_BIG;
+  const float mref = (LSE && !fresh) ? st.mx : 0.f;
+  const float off = qp.y - mref;
   float L[32];
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
     const float4 cp = *reinterpret_cast<const float4*>(colp + c);  // {c0, lq0, c1, lq1}, warp-broadcast
-    float l0 = fmaf(qp.x, __uint_as_float(v[c]) + cp.x, qp.y);
-    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]) + cp.z, qp.y);
+    float l0 = fmaf(qp.x, __uint_as_float(v[c]) + cp.x, off);
+    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]) + cp.z, off);
     if (LOGQ) {
       l0 -= cp.y;
       l1 -= cp.w;
@@ -140,48 +147,68 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
     L[c] = l0;
     L[c + 1] = l1;
   }
-  if (LM & (LM_INFONCE | LM_MINE)) {
-    float cm = L[0];
+  if (LSE) {
+    float m0 = fmaxf(L[0], L[4]), m1 = fmaxf(L[1], L[5]), m2 = fmaxf(L[2], L[6]), m3 = fmaxf(L[3], L[7]);
 #pragma unroll
-    for (int c = 1; c < 32; ++c) cm = fmaxf(cm, L[c]);
-    if (cm > st.mx) {
-      st.se *= ex2f(st.mx - cm);
-      st.mx = cm;
+    for (int c = 8; c < 32; c += 4) {
+      m0 = fmaxf(m0, L[c]);
+      m1 = fmaxf(m1, L[c + 1]);
+      m2 = fmaxf(m2, L[c + 2]);
+      m3 = fmaxf(m3, L[c + 3]);
     }
-    float s0 = 0.f, s1 = 0.f;
+    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // relative to mref
+    if ((cm > 0.f || fresh) && cm > -INFINITY) {
+      // new running maximum: rebase this chunk and the accumulated sum
+      const float nmx = mref + cm;
+      st.se *= ex2f(st.mx - nmx);                            // fresh: ex2(-1e30 - x) = 0
+      st.mx = nmx;
 #pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      s0 += ex2f(L[c] - st.mx);
-      s1 += ex2f(L[c + 1] - st.mx);
+      for (int c = 0; c < 32; ++c) L[c] -= cm;
     }
-    st.se += s0 + s1;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      s0 += ex2f(L[c]);
+      s1 += ex2f(L[c + 1]);
+      s2 += ex2f(L[c + 2]);
+      s3 += ex2f(L[c + 3]);
+    }
+    st.se += (s0 + s1) + (s2 + s3);
   }
-  if (LM & LM_CONTR) {
-    float s0 = 0.f, s1 = 0.f;
+  if (OTHER) {
+    // the remaining losses need absolute logits: add the reference back (0 unless an LSE loss is also on)
+    const float back = LSE ? st.mx : 0.f;   // L is now relative to st.mx
+    if (LM & LM_CONTR) {
+      const float o = back + qp.w;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      s0 += fmaxf(L[c] + qp.w, 0.f);
-      s1 += fmaxf(L[c + 1] + qp.w, 0.f);
+      for (int c = 0; c < 32; c += 4) {
+        s0 += fmaxf(L[c] + o, 0.f);
+        s1 += fmaxf(L[c + 1] + o, 0.f);
+        s2 += fmaxf(L[c + 2] + o, 0.f);
+        s3 += fmaxf(L[c + 3] + o, 0.f);
+      }
+      st.csum += (s0 + s1) + (s2 + s3);
     }
-    st.csum += s0 + s1;
-  }
-  if (LM & (LM_HINGE | LM_LOGI)) {
-    float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
+    if (LM & (LM_HINGE | LM_LOGI)) {
+      const float o = back + qp.z;
+      float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const float x0 = L[c] + qp.z, x1 = L[c + 1] + qp.z;
-      if (LM & LM_HINGE) {
-        h0 += fmaxf(x0, 0.f);
-        h1 += fmaxf(x1, 0.f);
+      for (int c = 0; c < 32; c += 2) {
+        const float x0 = L[c] + o, x1 = L[c + 1] + o;
+        if (LM & LM_HINGE) {
+          h0 += fmaxf(x0, 0.f);
+          h1 += fmaxf(x1, 0.f);
+        }
+        if (LM & LM_LOGI) {
+          // softplus in log2 units: log2(1 + 2^x); for x > 40 it equals x to fp32 precision
+          g0 += x0 > 40.f ? x0 : lg2f(1.f + ex2f(x0));
+          g1 += x1 > 40.f ? x1 : lg2f(1.f + ex2f(x1));
+        }
       }
-      if (LM & LM_LOGI) {
-        // softplus in log2 units: log2(1 + 2^x); for x > 40 it equals x to fp32 precision
-        g0 += x0 > 40.f ? x0 : lg2f(1.f + ex2f(x0));
-        g1 += x1 > 40.f ? x1 : lg2f(1.f + ex2f(x1));
-      }
+      st.hsum += h0 + h1;
+      st.lsum += g0 + g1;
     }
-    st.hsum += h0 + h1;
-    st.lsum += g0 + g1;
   }
   st.cnt += static_cast<float>(32 - __popc(mw));
 }
@@ -455,37 +482,58 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     unsigned long long* cbuf = nullptr;
     if (MODE == MODE_TOPK) cbuf = p.cand + out_row * p.cap;
 
+    // Per-tile side inputs (mask words of this row, parameters of the tile's columns) come from global
+    // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
+    constexpr int CSHARE = (CPAR + EPI_HALVES - 1) / EPI_HALVES;   // column-parameter floats this thread stages
+    const int jl = e_tid & (BN - 1);
+    const bool use_cpar = (MODE == MODE_FWD || MODE == MODE_GRAD || MODE == MODE_TOPK) && p.cpar != nullptr;
+    auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
+      const int jt = tile * BN;
+      if (mrow != nullptr) {
+        const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (jt >> 5) + 2 * half);
+        m0 = m2.x;
+        m1 = m2.y;
+      } else {  // no mask given: only the column bound applies
+        const int rem0 = p.nC - (jt + 64 * half), rem1 = rem0 - 32;
+        m0 = rem0 >= 32 ? 0u : (rem0 <= 0 ? 0xffffffffu : (0xffffffffu << rem0));
+        m1 = rem1 >= 32 ? 0u : (rem1 <= 0 ? 0xffffffffu : (0xffffffffu << rem1));
+      }
+    };
+    auto fetch_cpar = [&](int tile, float (&cv)[CSHARE]) {
+      const int j = tile * BN + jl;
+#pragma unroll
+      for (int u = 0; u < CSHARE; ++u) {
+        const int i = (e_tid >> 7) + u * EPI_HALVES;
+        cv[u] = (use_cpar && i < CPAR && j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
+      }
+    };
+    uint32_t mw0_next = 0u, mw1_next = 0u;
+    float cpar_next[CSHARE];
+    fetch_mask(t_begin, mw0_next, mw1_next);
+    fetch_cpar(t_begin, cpar_next);
+
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       const int j0 = (t_begin + t) * BN;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
       if (t > 0) named_bar_sync(2, EPI_THREADS);
-      if (MODE == MODE_FWD || MODE == MODE_GRAD || (MODE == MODE_TOPK)) {
-        const int jl = e_tid & (BN - 1);
-        const int j = j0 + jl;
-        if (p.cpar != nullptr) {
-          for (int i = e_tid >> 7; i < CPAR; i += EPI_HALVES)
-            cpar_s[jl * CPAR + i] = (j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
+      if (use_cpar) {
+#pragma unroll
+        for (int u = 0; u < CSHARE; ++u) {
+          const int i = (e_tid >> 7) + u * EPI_HALVES;
+          if (i < CPAR) cpar_s[jl * CPAR + i] = cpar_next[u];
         }
       }
-      uint32_t mw[2] = {0u, 0u};
-      if (mrow != nullptr) {
-        const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (j0 >> 5) + 2 * half);
-        mw[0] = m2.x; mw[1] = m2.y;
-      } else {
-        // no mask given: only the column bound applies
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int rem = p.nC - (j0 + 32 * (2 * half + c));
-          mw[c] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
-        }
+      const uint32_t mw0 = mw0_next, mw1 = mw1_next;
+      if (t + 1 < T) {
+        fetch_mask(t_begin + t + 1, mw0_next, mw1_next);
+        fetch_cpar(t_begin + t + 1, cpar_next);
       }
       named_bar_sync(1, EPI_THREADS);
 
       mbar_wait(&bars->s_full[b], (t >> 1) & 1);
       tc_fence_after();
-      if (HAS_G) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
 
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
@@ -493,7 +541,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(b * BN + ch * 32), v);
         tmem_ld_wait();
-        const uint32_t mwc = mw[cc];
+        const uint32_t mwc = cc == 0 ? mw0 : mw1;
 
         if (MODE == MODE_FWD) {
           const float4 qp = make_float4(rp_reg[0], rp_reg[1], rp_reg[2], rp_reg[3]);
@@ -532,6 +580,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             rg += g[0] + g[1];
             pk[c >> 1] = pack_bf16x2(g[0], g[1]);
           }
+          // the previous tile's G must have been consumed by its second MMA before it is overwritten
+          if (cc == 0) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
           store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_DEBUG) {
           uint32_t pk[16];
@@ -548,6 +598,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             rg += a + bb;
             pk[c >> 1] = pack_bf16x2(a, bb);
           }
+          if (cc == 0) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
           store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_TOPK) {
           // key per element (larger = better); masked / out-of-range columns get key 0
