@@ -829,7 +829,7 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
                     const void* rows, const void* cols, float* s_out, float* acc_out, void* workspace,
                     size_t workspace_bytes, void* stream) {
   if (num_rows <= 0 || num_cols <= 0 || dim <= 0 || dim > 256) return fail(XB_ERR_INVALID_ARG, "bad sizes");
-  if (!rows || !cols || !s_out || !acc_out || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (!rows || !cols || !acc_out || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
   DebugWs w;
   if (!debug_ws_layout(num_rows, num_cols, dim, compute, &w)) return fail(XB_ERR_UNSUPPORTED, "does not fit shared memory");
   if (workspace_bytes < w.total) return fail(XB_ERR_WORKSPACE, "workspace too small");

@@ -79,6 +79,11 @@ struct SweepSmemLayout {
   uint32_t r_off, c_off, g_off, par_off, bar_off, total;
 };
 
+// The gradient tile G is the A operand of the second MMA.  It lives in TMEM (columns after the accumulator,
+// double-buffered when kp <= 128) whenever 256 + kp + 64 <= 512 columns; only kp = 256 stages it in shared memory.
+__host__ __device__ constexpr bool g_in_tmem(int kp) { return kp <= 192; }
+__host__ __device__ constexpr int g_tmem_bufs(int kp) { return kp <= 128 ? 2 : 1; }
+
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool has_g,
                                                              int cpar_floats) {
   SweepSmemLayout L;
@@ -86,7 +91,7 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, 
   L.r_off = 0;
   L.c_off = tile;
   L.g_off = L.c_off + nstages * tile;
-  L.par_off = L.g_off + (has_g ? 2u * BLOCK_BYTES : 0u);
+  L.par_off = L.g_off + ((has_g && !g_in_tmem(kp)) ? 2u * BLOCK_BYTES : 0u);
   const uint32_t par_bytes = static_cast<uint32_t>(BN) * cpar_floats * 4u;  // column parameters of one tile
   L.bar_off = L.par_off + par_bytes;
   L.total = L.bar_off + 256u;  // barriers + tmem pointer
@@ -100,8 +105,8 @@ struct SweepBars {
   uint64_t c_empty[MAX_STAGES];
   uint64_t s_full[2];
   uint64_t s_empty[2];
-  uint64_t g_full;
-  uint64_t g_empty;
+  uint64_t g_full[2];
+  uint64_t g_empty[2];
   uint64_t acc_full;
   uint32_t tmem_base;
 };
@@ -347,6 +352,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const int nblk = kb_n * p.parts;
   const uint32_t tile_bytes = static_cast<uint32_t>(nblk) * BLOCK_BYTES;
   const int NS = p.nstages;
+  const bool g_tmem = HAS_G && g_in_tmem(p.kp);
+  const int g_bufs = g_tmem ? g_tmem_bufs(p.kp) : 1;
+  const uint32_t g_col0 = TMEM_ACC_COL + static_cast<uint32_t>(p.kp);   // TMEM columns of the G buffers
 
   const int chunk = blockIdx.x;
   const int rb = blockIdx.y;
@@ -364,8 +372,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       mbar_init(&bars->s_full[b], 1);
       mbar_init(&bars->s_empty[b], EPI_THREADS);
     }
-    mbar_init(&bars->g_full, EPI_THREADS);
-    mbar_init(&bars->g_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->g_full[b], EPI_THREADS);
+      mbar_init(&bars->g_empty[b], 1);
+    }
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmR);
@@ -397,37 +407,57 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0 && T > 0) {
+    // The whole warp runs this loop in lock-step (uniform control flow, every lane polls the barriers); one
+    // elected lane issues the tcgen05 instructions.  One thread feeds the tensor core for the whole CTA, so the
+    // per-MMA issue cost is kept to a couple of 32-bit adds.
+    if (T > 0) {
       const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
       const uint32_t idesc_g = umma_idesc_bf16(BM, static_cast<uint32_t>(p.kp), 0, 1);
-      const uint32_t sR_a = smem_u32(sR), sC_a = smem_u32(sC), sG_a = smem_u32(sG);
+      const uint32_t r_lo = umma_desc_lo(smem_u32(sR), 16);                       // K-major operand tiles
+      const uint32_t c_lo0 = umma_desc_lo(smem_u32(sC), 16);
+      const uint32_t cmn_lo0 = umma_desc_lo(smem_u32(sC), BLOCK_BYTES);           // same tiles read MN-major
+      const uint32_t g_lo = umma_desc_lo(smem_u32(sG), 16);
+      const uint32_t tile_lo = tile_bytes >> 4;                                   // descriptor units are 16 B
+      const uint32_t blk_lo = BLOCK_BYTES >> 4;
+      const uint32_t part_lo = static_cast<uint32_t>(kb_n) * blk_lo;
+      const uint32_t acc_tmem = tmem_base + TMEM_ACC_COL;
 
       auto issue_scores = [&](int t) {
         const int b = t & 1, s = t % NS;
         mbar_wait(&bars->s_empty[b], ((t >> 1) & 1) ^ 1);
         mbar_wait(&bars->c_full[s], (t / NS) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b) * BN;
-        const uint32_t c_base = sC_a + static_cast<uint32_t>(s) * tile_bytes;
-        uint32_t acc = 0;
-        // split operands: (lo x hi) + (hi x lo) + (hi x hi); the lo x lo term (2^-18 relative) is dropped
-        const int npairs = p.parts == 1 ? 1 : 3;
-        for (int pr = 0; pr < npairs; ++pr) {
-          const int rp = (p.parts == 2 && pr == 0) ? 1 : 0;
-          const int cp = (p.parts == 2 && pr == 1) ? 1 : 0;
-          for (int kb = 0; kb < kb_n; ++kb) {
-            const uint32_t a_blk = sR_a + static_cast<uint32_t>(rp * kb_n + kb) * BLOCK_BYTES;
-            const uint32_t b_blk = c_base + static_cast<uint32_t>(cp * kb_n + kb) * BLOCK_BYTES;
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b) * BN;
+          const uint32_t c_lo = c_lo0 + static_cast<uint32_t>(s) * tile_lo;
+          uint32_t acc = 0;
+          if (p.parts == 1) {
+            for (int kb = 0; kb < kb_n; ++kb) {
+              const uint32_t a = r_lo + kb * blk_lo, bq = c_lo + kb * blk_lo;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_tmem, umma_smem_desc(a_blk + k * 32, 16, 1024), umma_smem_desc(b_blk + k * 32, 16, 1024),
-                        idesc_s, acc);
-              acc = 1;
+              for (int k = 0; k < 4; ++k) {
+                umma_ss_lo(d_tmem, a + 2 * k, bq + 2 * k, idesc_s, acc);
+                acc = 1;
+              }
+            }
+          } else {
+            // split operands: (lo x hi) + (hi x lo) + (hi x hi); the lo x lo term (2^-18 relative) is dropped
+            for (int pr = 0; pr < 3; ++pr) {
+              const uint32_t a0 = r_lo + (pr == 0 ? part_lo : 0u), b0 = c_lo + (pr == 1 ? part_lo : 0u);
+              for (int kb = 0; kb < kb_n; ++kb) {
+                const uint32_t a = a0 + kb * blk_lo, bq = b0 + kb * blk_lo;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_ss_lo(d_tmem, a + 2 * k, bq + 2 * k, idesc_s, acc);
+                  acc = 1;
+                }
+              }
             }
           }
+          umma_commit(&bars->s_full[b]);
+          if (!HAS_G) umma_commit(&bars->c_empty[s]);
         }
-        umma_commit(&bars->s_full[b]);
-        if (!HAS_G) umma_commit(&bars->c_empty[s]);
+        __syncwarp();
       };
 
       mbar_wait(&bars->r_full, 0);
@@ -436,25 +466,42 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         if (t + 1 < T) issue_scores(t + 1);
         if (HAS_G) {
           const int s = t % NS;
-          mbar_wait(&bars->g_full, t & 1);
+          const int gb = g_bufs == 2 ? (t & 1) : 0;
+          mbar_wait(&bars->g_full[gb], (t / g_bufs) & 1);
           tc_fence_after();
-          const uint32_t c_base = sC_a + static_cast<uint32_t>(s) * tile_bytes;
-#pragma unroll 1
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            // A = G tile, K-major (K = column index of the score tile)
-            const uint64_t da = umma_smem_desc(sG_a + (kk >> 2) * BLOCK_BYTES + (kk & 3) * 32, 16, 1024);
-            for (int pt = 0; pt < p.parts; ++pt) {
-              // B = column-operand tile read MN-major: N = embedding dim, K = tile row (16 rows = 2048 B)
-              const uint64_t db =
-                  umma_smem_desc(c_base + static_cast<uint32_t>(pt * kb_n) * BLOCK_BYTES + kk * 2048, BLOCK_BYTES, 1024);
-              umma_bf16(tmem_base + TMEM_ACC_COL, da, db, idesc_g, (t | kk | pt) != 0 ? 1u : 0u);
+          if (elect_one()) {
+            // acc[128 x kp] += G[128 x 128] . C_tile[128 x kp]: B = the column-operand tile read MN-major
+            // (N = embedding dim, K = tile row; 16 rows = 2048 B), hi part then lo part in split mode.
+            const uint32_t b_lo = cmn_lo0 + static_cast<uint32_t>(s) * tile_lo;
+            uint32_t acc = t != 0 ? 1u : 0u;
+            if (g_tmem) {
+              const uint32_t a_tmem = tmem_base + g_col0 + static_cast<uint32_t>(gb * 64);   // 8 columns per K-step
+              for (int pt = 0; pt < p.parts; ++pt) {
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {
+                  umma_ts_lo(acc_tmem, a_tmem + kk * 8, b_lo + pt * part_lo + kk * 128, idesc_g, acc);
+                  acc = 1;
+                }
+              }
+            } else {
+              for (int pt = 0; pt < p.parts; ++pt) {
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {
+                  // A = G tile in shared memory, K-major: block kk/4, 32 B per K-step inside the block
+                  umma_ss_lo(acc_tmem, g_lo + (kk >> 2) * blk_lo + (kk & 3) * 2, b_lo + pt * part_lo + kk * 128, idesc_g,
+                             acc);
+                  acc = 1;
+                }
+              }
             }
+            umma_commit(&bars->g_empty[gb]);
+            umma_commit(&bars->c_empty[s]);
           }
-          umma_commit(&bars->g_empty);
-          umma_commit(&bars->c_empty[s]);
+          __syncwarp();
         }
       }
-      if (HAS_G) umma_commit(&bars->acc_full);
+      if (HAS_G && elect_one()) umma_commit(&bars->acc_full);
+      __syncwarp();
     }
   } else if (T > 0) {
     // ======================================================================== epilogue warps
@@ -514,6 +561,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
+      const int gb = g_bufs == 2 ? (t & 1) : 0;
       const int j0 = (t_begin + t) * BN;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
@@ -580,9 +628,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             rg += g[0] + g[1];
             pk[c >> 1] = pack_bf16x2(g[0], g[1]);
           }
-          // the previous tile's G must have been consumed by its second MMA before it is overwritten
-          if (cc == 0) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
-          store_g_chunk(sG, row_l, ch * 32, pk);
+          // the G buffer must have been consumed by its previous second MMA before it is overwritten
+          if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
+          if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
+          else store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_DEBUG) {
           uint32_t pk[16];
 #pragma unroll
@@ -598,8 +647,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             rg += a + bb;
             pk[c >> 1] = pack_bf16x2(a, bb);
           }
-          if (cc == 0) mbar_wait(&bars->g_empty, (t & 1) ^ 1);
-          store_g_chunk(sG, row_l, ch * 32, pk);
+          if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
+          if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
+          else store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_TOPK) {
           // key per element (larger = better); masked / out-of-range columns get key 0
           uint32_t key[32];
@@ -660,8 +710,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       tc_fence_before();
       mbar_arrive(&bars->s_empty[b]);
       if (HAS_G) {
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->g_full);
+        if (g_tmem) {
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(&bars->g_full[gb]);
       }
     }
 
