@@ -155,14 +155,30 @@ def loss_step_fn(module, inp: dict):  # noqa: ANN001, ANN201
     q = inp["user_embed"].detach().requires_grad_(True)
     v = inp["item_embed"].detach().requires_grad_(True)
 
-    def step() -> torch.Tensor:
-        q.grad = None
-        v.grad = None
+    def step() -> tuple:
         loss = module(q, v, inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
-        loss.backward()
-        return loss
+        dq, dv = torch.autograd.grad(loss, (q, v))
+        return loss, dq, dv
 
     return step
+
+
+def graphed(step_fn):  # noqa: ANN001, ANN201
+    """Capture one step (module forward + backward) into a CUDA graph; returns the replay callable.
+    The library allocates nothing and never synchronises, so the whole step is capturable."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step_fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = step_fn()
+    torch.cuda.synchronize()
+    graph.keep = keep  # outputs live in the graph's pool
+    return graph.replay
 
 
 def cpu_reference_rate(steps: int, warmup: int, name: str = HEADLINE_LOSS) -> dict:
@@ -291,6 +307,7 @@ def main() -> None:  # noqa: PLR0915
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (skip per-loss / retrieval / gather / cpu baseline)")
     ap.add_argument("--retrieval-items", type=int, default=8_000_000, help="catalog rows of the retrieval extra (config 5 is 100,000,000)")
     ap.add_argument("--retrieval-queries", type=int, default=65_536)
@@ -316,8 +333,10 @@ def main() -> None:  # noqa: PLR0915
 
     inp = make_c2(device, rank, torch.bfloat16)
     module = getattr(xfmr_b200, HEADLINE_LOSS)(sigma=SIGMA, margin=MARGIN)
-    step = loss_step_fn(module, inp)
+    eager_step = loss_step_fn(module, inp)
     flush_buf = torch.zeros(64 << 20, dtype=torch.float32, device=device)
+    eager_ms = statistics.mean(timed_steps(eager_step, min(args.steps, 50), warmup, flush_buf))
+    step = eager_step if args.no_graph else graphed(eager_step)
 
     # ---- device-resident timing (value) + live sweep-kernel timing (roofline)
     clocks = ClockSampler(local_rank)
@@ -328,13 +347,17 @@ def main() -> None:  # noqa: PLR0915
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    _lib.launch_count(reset=True)
-    _lib.sweep_timing(True)
     clocks.mark_begin()
     times = timed_steps(step, args.steps, 0, flush_buf)
     torch.cuda.synchronize()
     clocks.mark_end()
     clocks.stop()
+    # live duration of the dominant kernel (the three sweep launches of a step): CUDA events recorded by the
+    # library on the launch stream, over the same number of eager steps (events cannot be read from a replay)
+    _lib.launch_count(reset=True)
+    _lib.sweep_timing(True)
+    timed_steps(eager_step, args.steps, 0, flush_buf)
+    torch.cuda.synchronize()
     sweep_ms_total, sweep_count = _lib.sweep_timing_read()
     _lib.sweep_timing(False)
     launches = _lib.launch_count()
@@ -356,7 +379,7 @@ def main() -> None:  # noqa: PLR0915
         v = dev["item_embed"].requires_grad_(True)
         loss = module(q, v, dev["target"], item_idx=dev["item_idx"], pos_idx=dev["pos_idx"])
         loss.backward()
-        return float(loss)  # device -> host read of the step's result (synchronises)
+        return float(loss.detach())  # device -> host read of the step's result (synchronises)
 
     for _ in range(3):
         e2e_step()
@@ -395,11 +418,13 @@ def main() -> None:  # noqa: PLR0915
                         "(InfomationNoiseContrastiveEstimationLoss) fwd+bwd through the drop-in module",
             "sigma": SIGMA, "margin": MARGIN, "num_negatives": 0,
             "l2": "flushed between steps (256 MiB read+write)",
+            "launch": "eager" if args.no_graph else "CUDA-graph replay of the module's forward+backward (eager ms in eager_ms_per_step)",
             "parallelism": f"dp{world} (users sharded, no data-path collective)",
         },
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        "eager_ms_per_step": eager_ms,
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
@@ -414,10 +439,10 @@ def main() -> None:  # noqa: PLR0915
         per_loss = {}
         for name in xfmr_b200.LOSS_SLOTS:
             m = getattr(xfmr_b200, name)(sigma=SIGMA, margin=MARGIN)
-            t = timed_steps(loss_step_fn(m, inp), 8, 3, flush_buf)
+            t = timed_steps(graphed(loss_step_fn(m, inp)), 8, 3, flush_buf)
             per_loss[name] = {"ms_per_step": statistics.median(t), "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
         mined = xfmr_b200.PairwiseHingeLoss(num_negatives=4, sigma=SIGMA, margin=MARGIN)  # the reference's training default
-        t = timed_steps(loss_step_fn(mined, inp), 8, 3, flush_buf)
+        t = timed_steps(graphed(loss_step_fn(mined, inp)), 8, 3, flush_buf)
         per_loss["PairwiseHingeLoss[num_negatives=4]"] = {"ms_per_step": statistics.median(t),
                                                            "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
 

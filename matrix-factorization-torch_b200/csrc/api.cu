@@ -191,13 +191,11 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
   const int words = mask_words_for(ncols), words_t = mask_words_for(nrows);
   const int rows_pad = cdiv(nrows, BM) * BM, cols_pad = cdiv(ncols, BM) * BM;
   {
-    const size_t total = static_cast<size_t>(rows_pad) * words;
-    mask_init_kernel<<<cdiv(total, 256), 256, 0, st>>>(mask, rows_pad, words, nrows, ncols);
+    mask_init_kernel<<<dim3(rows_pad, cdiv(words / 4, 128)), 128, 0, st>>>(mask, rows_pad, words, nrows, ncols);
     XB_LAUNCHED();
   }
   if (mask_t != nullptr) {
-    const size_t total = static_cast<size_t>(cols_pad) * words_t;
-    mask_init_kernel<<<cdiv(total, 256), 256, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
+    mask_init_kernel<<<dim3(cols_pad, cdiv(words_t / 4, 128)), 128, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
     XB_LAUNCHED();
   }
   const bool any_ids = (row_ids0 != nullptr) || (row_lists != nullptr && list_len > 0);
@@ -226,7 +224,7 @@ struct LossWs {
   bool mining;
   SweepPlan fwd, gq, gi;   // forward / mining sweep, dQ sweep, dI sweep
   size_t qprep, iprep, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
-      ueff, qg, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, total;
+      ueff, qg, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
 
 static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
@@ -264,20 +262,21 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->mask = take(sizeof(uint32_t) * w->B_pad * static_cast<size_t>(w->words));
   w->mask_t = take(sizeof(uint32_t) * w->N_pad * static_cast<size_t>(w->words_t));
   w->pm_ws = take(pair_mask_ws(N).total);
-  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad);
+  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
   w->rowstat = take(sizeof(float4) * B);
   w->rowloss = take(sizeof(float) * 7 * B);
   w->ueff = take(sizeof(float) * 8);
+  w->redpart = take(sizeof(double) * XB_NUM_LOSSES * cdiv(B, LOSS_RED_ROWS));
   w->qg = take(sizeof(float) * 12 * B);
   const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
   w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
-  w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * EPI_HALVES * w->B_pad);
+  w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * MAX_EPI_PARTS * w->B_pad);
   w->acci = take(sizeof(float) * static_cast<size_t>(ni) * w->N_pad * w->kp);
-  w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * EPI_HALVES * w->N_pad);
+  w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * MAX_EPI_PARTS * w->N_pad);
   w->gdiag = take(sizeof(float) * B);
   if (w->mining) {
-    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad * MINE_CAP);
-    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * EPI_HALVES * w->B_pad);
+    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad * MINE_CAP);
+    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
     w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w->Kf);
     w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
     w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
@@ -377,7 +376,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
                                      w.gq.smem, st));
       nq = w.gq.nchunks;
-      nq_sub = nq * EPI_HALVES;
+      nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
     }
     {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
@@ -390,7 +389,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
-      ni_sub = ni * EPI_HALVES;
+      ni_sub = ni * epi_parts(MODE_GRAD, lm, false);
     }
   }
   grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
@@ -530,7 +529,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
       p.out_stats = reinterpret_cast<float*>(ws + w.part);
       XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
-      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * EPI_HALVES, p.out_stats, desc->sigma,
+      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
                                                      reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
       XB_LAUNCHED();
@@ -546,7 +545,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
-            B, p.nR_pad, w.fwd.nchunks * EPI_HALVES, MINE_CAP, w.Kf, p.cand, p.cand_cnt,
+            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), MINE_CAP, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
         XB_LAUNCHED();
       }
@@ -569,8 +568,14 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                                    reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
     XB_LAUNCHED();
   }
-  loss_reduce_kernel<<<XB_NUM_LOSSES, 256, 0, st>>>(B, rowloss, desc->loss_mask, losses_out);
-  XB_LAUNCHED();
+  {
+    const int nblk = cdiv(B, LOSS_RED_ROWS);
+    double* partial = reinterpret_cast<double*>(ws + w.redpart);
+    loss_reduce1_kernel<<<dim3(nblk, XB_NUM_LOSSES), 256, 0, st>>>(B, rowloss, partial);
+    XB_LAUNCHED();
+    loss_reduce2_kernel<<<1, 32, 0, st>>>(nblk, partial, desc->loss_mask, losses_out);
+    XB_LAUNCHED();
+  }
   return XB_OK;
 }
 
@@ -641,8 +646,8 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->qprep = take(rowb * d->num_queries);
   w->iprep = take(w->items_inplace ? 0 : rowb * static_cast<size_t>(d->num_items));
-  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * EPI_HALVES * w->Q_pad * w->cap);
-  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * EPI_HALVES * w->Q_pad);
+  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * MAX_EPI_PARTS * w->Q_pad * w->cap);
+  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * MAX_EPI_PARTS * w->Q_pad);
   w->ent = take(sizeof(unsigned long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->scores = take(sizeof(float) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->ids = take(sizeof(long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
@@ -709,7 +714,7 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
   cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(
-      Q, p.nR_pad, w.plan.nchunks * EPI_HALVES, w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
+      Q, p.nR_pad, w.plan.nchunks * epi_parts(MODE_TOPK, 0, true), w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
   XB_LAUNCHED();
   float* stmp = reinterpret_cast<float*>(ws + w.scores);
   long long* itmp = reinterpret_cast<long long*>(ws + w.ids);
@@ -812,7 +817,7 @@ bool debug_ws_layout(int nR, int nC, int dim, int compute, DebugWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->rprep = off; off = align_up(off + rowb * nR, 256);
   w->cprep = off; off = align_up(off + rowb * nC, 256);
-  w->rs = off; off = align_up(off + sizeof(float) * 2 * EPI_HALVES * cdiv(nR, BM) * BM, 256);
+  w->rs = off; off = align_up(off + sizeof(float) * 2 * MAX_EPI_PARTS * cdiv(nR, BM) * BM, 256);
   w->total = off;
   return w->plan.ok;
 }

@@ -111,19 +111,23 @@ __global__ void item_params_kernel(int N, const float* __restrict__ in2, const f
 // ------------------------------------------------------------------------------------------------
 __global__ void mask_init_kernel(uint32_t* __restrict__ mask, int rows_pad, int words, int rows_valid,
                                  int cols_valid) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(rows_pad) * words;
-  if (i >= total) return;
-  const int r = static_cast<int>(i / words);
-  const int w = static_cast<int>(i % words);
-  uint32_t v;
+  // grid = (rows_pad, ceil(words/4 / blockDim)); every thread writes one 16-byte group of a row
+  const int r = blockIdx.x;
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;   // group of 4 words
+  if (g * 4 >= words) return;
+  uint4 v;
   if (r >= rows_valid) {
-    v = 0xffffffffu;
+    v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   } else {
-    const int rem = cols_valid - w * 32;
-    v = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rem = cols_valid - (g * 4 + i) * 32;
+      w[i] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  mask[i] = v;
+  *reinterpret_cast<uint4*>(mask + static_cast<size_t>(r) * words + g * 4) = v;
 }
 
 __device__ __forceinline__ uint32_t hash64(long long id) {
@@ -238,20 +242,30 @@ __global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __
   write_row_losses(row, B, sigma, rowinfo[row], diag[row], cnt, csum, hsum, lsum, lseM2, rowstat, rowloss);
 }
 
-// deterministic sum of each of the 7 row-loss vectors: one block per loss
-__global__ void loss_reduce_kernel(int B, const float* __restrict__ rowloss, uint32_t loss_mask,
-                                   float* __restrict__ losses) {
+// deterministic sum of each of the 7 row-loss vectors in two fixed-shape stages (fp64):
+// stage 1: grid (nblk, 7) -> partial[l][blk];  stage 2: one block -> losses[7]
+constexpr int LOSS_RED_ROWS = 1024;   // rows per stage-1 block
+__global__ void loss_reduce1_kernel(int B, const float* __restrict__ rowloss, double* __restrict__ partial) {
   __shared__ double sh[256];
-  const int l = blockIdx.x;
+  const int l = blockIdx.y, blk = blockIdx.x;
+  const int lo = blk * LOSS_RED_ROWS, hi = min(lo + LOSS_RED_ROWS, B);
   double acc = 0.0;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) acc += static_cast<double>(rowloss[static_cast<size_t>(l) * B + i]);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += static_cast<double>(rowloss[static_cast<size_t>(l) * B + i]);
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) losses[l] = ((loss_mask >> l) & 1u) ? static_cast<float>(sh[0]) : 0.f;
+  if (threadIdx.x == 0) partial[static_cast<size_t>(l) * gridDim.x + blk] = sh[0];
+}
+__global__ void loss_reduce2_kernel(int nblk, const double* __restrict__ partial, uint32_t loss_mask,
+                                    float* __restrict__ losses) {
+  const int l = threadIdx.x;
+  if (l >= 7) return;
+  double acc = 0.0;
+  for (int i = 0; i < nblk; ++i) acc += partial[static_cast<size_t>(l) * nblk + i];
+  losses[l] = ((loss_mask >> l) & 1u) ? static_cast<float>(acc) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,9 +331,29 @@ __device__ __forceinline__ void store_out<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// four consecutive prepared values (k % 4 == 0): 8-byte loads of the hi (and lo) parts
+__device__ __forceinline__ float4 prepped_val4(const __nv_bfloat16* row, int kp, int parts, int k) {
+  const uint2 h = *reinterpret_cast<const uint2*>(row + k);
+  float4 v = make_float4(bf_lo(h.x), bf_hi(h.x), bf_lo(h.y), bf_hi(h.y));
+  if (parts == 2) {
+    const uint2 l = *reinterpret_cast<const uint2*>(row + kp + k);
+    v.x += bf_lo(l.x); v.y += bf_hi(l.x); v.z += bf_lo(l.y); v.w += bf_hi(l.y);
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ void store_out4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store_out4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void store_out4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
 // dQ_i = sum_j G_ij v_j + G_ii v_i - (RG_i + G_ii) q_i          (dS/dq = v - q)
 // G_ii = -target*sigma*uA - RGH_i + a*w*(uI*(p_ii - 1) - uM)
-// One warp per query row.  gdiag[i] = G_ii is kept for the item-side finalisation.
+// One warp per query row, four columns per lane (d % 4 == 0 fast path).  gdiag[i] = G_ii is kept for the
+// item-side finalisation.
 template <typename T>
 __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_pad, int nchunks, int nsub,
                                        const float* __restrict__ acc, const float* __restrict__ rs_part,
@@ -347,11 +381,26 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
   if (lane == 0) gdiag[row] = gii;
   const __nv_bfloat16* q = qp + static_cast<size_t>(row) * parts * kp;
   const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
-  for (int k = lane; k < d; k += 32) {
-    float s = 0.f;
-    for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
-    const float qv = prepped_val(q, kp, parts, k), vv = prepped_val(v, kp, parts, k);
-    store_out<T>(dq + static_cast<size_t>(row) * d + k, s + gii * vv - (rg + gii) * qv);
+  const float cq = rg + gii;
+  if ((d & 3) == 0) {
+    for (int k = lane * 4; k < d; k += 128) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < nchunks; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      const float4 qv = prepped_val4(q, kp, parts, k), vv = prepped_val4(v, kp, parts, k);
+      store_out4<T>(dq + static_cast<size_t>(row) * d + k,
+                    make_float4(s.x + gii * vv.x - cq * qv.x, s.y + gii * vv.y - cq * qv.y,
+                                s.z + gii * vv.z - cq * qv.z, s.w + gii * vv.w - cq * qv.w));
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      float s = 0.f;
+      for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
+      const float qv = prepped_val(q, kp, parts, k), vv = prepped_val(v, kp, parts, k);
+      store_out<T>(dq + static_cast<size_t>(row) * d + k, s + gii * vv - cq * qv);
+    }
   }
 }
 
@@ -366,15 +415,32 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
   if (row >= N) return;
   float cg = 0.f;
   for (int c = 0; c < nsub; ++c) cg += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
-  const float gjj = row < B ? gdiag[row] : 0.f;
+  const bool inb = row < B;
+  const float gjj = inb ? gdiag[row] : 0.f;
   const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
-  const __nv_bfloat16* q = qp + static_cast<size_t>(row < B ? row : 0) * parts * kp;
-  for (int k = lane; k < d; k += 32) {
-    float s = 0.f;
-    for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
-    const float vv = prepped_val(v, kp, parts, k);
-    const float qv = row < B ? prepped_val(q, kp, parts, k) : 0.f;
-    store_out<T>(di + static_cast<size_t>(row) * d + k, s - cg * vv + gjj * (qv - vv));
+  const __nv_bfloat16* q = qp + static_cast<size_t>(inb ? row : 0) * parts * kp;
+  if ((d & 3) == 0) {
+    for (int k = lane * 4; k < d; k += 128) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < nchunks; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      const float4 vv = prepped_val4(v, kp, parts, k);
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inb) qv = prepped_val4(q, kp, parts, k);
+      store_out4<T>(di + static_cast<size_t>(row) * d + k,
+                    make_float4(s.x - cg * vv.x + gjj * (qv.x - vv.x), s.y - cg * vv.y + gjj * (qv.y - vv.y),
+                                s.z - cg * vv.z + gjj * (qv.z - vv.z), s.w - cg * vv.w + gjj * (qv.w - vv.w)));
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      float s = 0.f;
+      for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
+      const float vv = prepped_val(v, kp, parts, k);
+      const float qv = inb ? prepped_val(q, kp, parts, k) : 0.f;
+      store_out<T>(di + static_cast<size_t>(row) * d + k, s - cg * vv + gjj * (qv - vv));
+    }
   }
 }
 

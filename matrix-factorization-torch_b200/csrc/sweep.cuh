@@ -13,10 +13,11 @@
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue: thread <-> (TMEM lane = tile row, column half).  Two epilogue warps share each SM
-// sub-partition so that one computes while the other waits on tcgen05.ld / MUFU / shared memory.
-// Per-row outputs are written per "sub-chunk" = 2 * column chunk + column half and merged by the finalisers.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then 4*EP epilogue warps:
+// thread <-> (TMEM lane = tile row, column part).  EP = 4 (16 epilogue warps, one 32-column chunk each) for the
+// single-loss forward / gradient variants, EP = 2 where register pressure is high (all-losses variants, top-k).
+// The epilogue is latency-bound (tcgen05.ld, MUFU, dependent FP chains), so warps per sub-partition matter.
+// Per-row outputs are written per "sub-chunk" = EP * column chunk + column part and merged by the finalisers.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,9 +31,7 @@ constexpr int BM = 128;                  // tile rows  (UMMA M)
 constexpr int BN = 128;                  // tile cols  (UMMA N of the score MMA)
 constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
 constexpr int BLOCK_BYTES = 128 * 128;   // one [128 rows x 64 bf16] SWIZZLE_128B block
-constexpr int EPI_HALVES = 2;              // epilogue warps come in two sets; set h owns tile columns [64h, 64h+64)
-constexpr int EPI_THREADS = 128 * EPI_HALVES;
-constexpr int SWEEP_THREADS = 64 + EPI_THREADS;
+constexpr int MAX_EPI_PARTS = 4;           // epilogue warps come in EP sets of 4; set p owns tile columns [128p/EP, 128(p+1)/EP)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_ACC_COL = 256;   // columns [256, 256+kp) hold the gradient accumulator
 constexpr int MAX_STAGES = 4;
@@ -43,6 +42,10 @@ enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 
 enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 16, LM_ALL = 31 };
 
 __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
+// number of epilogue column parts of a kernel variant
+__host__ __device__ constexpr int epi_parts(int mode, int lm, bool qrow) {
+  return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/) && qrow && lm != 0 && lm_single(lm)) ? 4 : 2;
+}
 // floats of per-query gradient parameters: single loss {a2, off, k, 0}; all {a2, (off,k) x 5, 0}
 __host__ __device__ constexpr int grad_qpar_floats(int lm) { return lm_single(lm) ? 4 : 12; }
 
@@ -63,12 +66,12 @@ struct SweepParams {
   const float* cpar;
   const uint32_t* mask; // [nR_pad][mask_words] bit (r, c) set => pair excluded (incl. c >= nC padding)
   int mask_words;       // 32-bit words per mask row = 4 * n_ctiles
-  float* out_stats;     // FWD : [2*nchunks][nR_pad][8]   GRAD: [2*nchunks][nR_pad][2] (row sums of G)
+  float* out_stats;     // FWD : [EP*nchunks][nR_pad][8]   GRAD: [EP*nchunks][nR_pad][2] (row sums of G)
   float* out_acc;       // GRAD: [nchunks][nR_pad][kp] partial accumulators
   float* dbg_s;         // DEBUG: [nR_pad][n_ctiles*BN] raw score tiles
   // TOPK
-  unsigned long long* cand;  // [2*nchunks][nR_pad][cap] candidate entries (key << 32 | ~col)
-  int* cand_cnt;             // [2*nchunks][nR_pad]
+  unsigned long long* cand;  // [EP*nchunks][nR_pad][cap] candidate entries (key << 32 | ~col)
+  int* cand_cnt;             // [EP*nchunks][nR_pad]
   int cap;                   // candidate buffer capacity per row (power of two, 64..1024)
   int keep;                  // entries kept by a compaction (<= cap/2)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
@@ -329,10 +332,13 @@ __device__ __forceinline__ uint32_t order_key(float f) {
 
 // =================================================================================================
 template <int MODE, int LM, bool QROW, bool LOGQ>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+__global__ void __launch_bounds__(64 + 128 * epi_parts(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
              const SweepParams p) {
   constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
+  constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
+  constexpr int CPT = 4 / EP;                      // 32-column chunks per epilogue thread and tile
+  constexpr int EPI_THREADS = 128 * EP;
   constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
   constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
 
@@ -506,13 +512,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   } else if (T > 0) {
     // ======================================================================== epilogue warps
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;               // column half of the tile this warp reduces
+    const int part = (warp - 2) >> 2;               // column part of the tile this warp reduces
     const int row_l = quad * 32 + lane;             // tile row == TMEM lane
     const int e_tid = threadIdx.x - 64;             // 0..255, used for cooperative parameter loads
     const int row = rb * BM + row_l;
     const bool row_ok = row < p.nR;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const size_t out_row = static_cast<size_t>(chunk * EPI_HALVES + half) * p.nR_pad + row;
+    const size_t out_row = static_cast<size_t>(chunk * EP + part) * p.nR_pad + row;
 
     float rp_reg[RPAR];
 #pragma unroll
@@ -531,17 +537,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
     // Per-tile side inputs (mask words of this row, parameters of the tile's columns) come from global
     // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
-    constexpr int CSHARE = (CPAR + EPI_HALVES - 1) / EPI_HALVES;   // column-parameter floats this thread stages
+    constexpr int CSHARE = (CPAR + EP - 1) / EP;   // column-parameter floats this thread stages
     const int jl = e_tid & (BN - 1);
     const bool use_cpar = (MODE == MODE_FWD || MODE == MODE_GRAD || MODE == MODE_TOPK) && p.cpar != nullptr;
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
       if (mrow != nullptr) {
-        const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (jt >> 5) + 2 * half);
-        m0 = m2.x;
-        m1 = m2.y;
+        if (CPT == 2) {
+          const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (jt >> 5) + 2 * part);
+          m0 = m2.x;
+          m1 = m2.y;
+        } else {
+          m0 = mrow[(jt >> 5) + part];
+          m1 = 0u;
+        }
       } else {  // no mask given: only the column bound applies
-        const int rem0 = p.nC - (jt + 64 * half), rem1 = rem0 - 32;
+        const int rem0 = p.nC - (jt + 32 * CPT * part), rem1 = rem0 - 32;
         m0 = rem0 >= 32 ? 0u : (rem0 <= 0 ? 0xffffffffu : (0xffffffffu << rem0));
         m1 = rem1 >= 32 ? 0u : (rem1 <= 0 ? 0xffffffffu : (0xffffffffu << rem1));
       }
@@ -550,7 +561,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const int j = tile * BN + jl;
 #pragma unroll
       for (int u = 0; u < CSHARE; ++u) {
-        const int i = (e_tid >> 7) + u * EPI_HALVES;
+        const int i = (e_tid >> 7) + u * EP;
         cv[u] = (use_cpar && i < CPAR && j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
       }
     };
@@ -569,7 +580,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if (use_cpar) {
 #pragma unroll
         for (int u = 0; u < CSHARE; ++u) {
-          const int i = (e_tid >> 7) + u * EPI_HALVES;
+          const int i = (e_tid >> 7) + u * EP;
           if (i < CPAR) cpar_s[jl * CPAR + i] = cpar_next[u];
         }
       }
@@ -584,8 +595,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       tc_fence_after();
 
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = 2 * half + cc;
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int ch = CPT * part + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(b * BN + ch * 32), v);
         tmem_ld_wait();
@@ -730,8 +741,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
       float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
-      const int per_half = p.kp / 32 / EPI_HALVES;   // kp is a multiple of 64
-      for (int cc = half * per_half; cc < (half + 1) * per_half; ++cc) {
+      for (int cc = part; cc < p.kp / 32; cc += EP) {   // accumulator chunks are dealt round-robin to the parts
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + TMEM_ACC_COL + static_cast<uint32_t>(cc * 32), v);
         tmem_ld_wait();

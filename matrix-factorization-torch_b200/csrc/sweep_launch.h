@@ -19,11 +19,11 @@ cudaError_t launch_sweep_debug(const CUtensorMap& tmR, const CUtensorMap& tmC, c
                                size_t smem, cudaStream_t st);
 
 template <typename K>
-inline cudaError_t launch_sweep_impl(K kernel, const CUtensorMap& tmR, const CUtensorMap& tmC, const SweepParams& p,
-                                     dim3 grid, size_t smem, cudaStream_t st) {
+inline cudaError_t launch_sweep_impl(K kernel, int mode, int lm, bool qrow, const CUtensorMap& tmR, const CUtensorMap& tmC,
+                                     const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kernel<<<grid, SWEEP_THREADS, smem, st>>>(tmR, tmC, p);
+  kernel<<<grid, 64 + 128 * epi_parts(mode, lm, qrow), smem, st>>>(tmR, tmC, p);
   return cudaGetLastError();
 }
 }  // namespace xb

@@ -2,11 +2,11 @@
 namespace xb {
 cudaError_t launch_sweep_topk(bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const SweepParams& p,
                               dim3 grid, size_t smem, cudaStream_t st) {
-  return logq ? launch_sweep_impl(sweep_kernel<MODE_TOPK, 0, true, true>, tmR, tmC, p, grid, smem, st)
-              : launch_sweep_impl(sweep_kernel<MODE_TOPK, 0, true, false>, tmR, tmC, p, grid, smem, st);
+  return logq ? launch_sweep_impl(sweep_kernel<MODE_TOPK, 0, true, true>, MODE_TOPK, 0, true, tmR, tmC, p, grid, smem, st)
+              : launch_sweep_impl(sweep_kernel<MODE_TOPK, 0, true, false>, MODE_TOPK, 0, true, tmR, tmC, p, grid, smem, st);
 }
 cudaError_t launch_sweep_debug(const CUtensorMap& tmR, const CUtensorMap& tmC, const SweepParams& p, dim3 grid,
                                size_t smem, cudaStream_t st) {
-  return launch_sweep_impl(sweep_kernel<MODE_DEBUG, 0, true, false>, tmR, tmC, p, grid, smem, st);
+  return launch_sweep_impl(sweep_kernel<MODE_DEBUG, 0, true, false>, MODE_DEBUG, 0, true, tmR, tmC, p, grid, smem, st);
 }
 }  // namespace xb
