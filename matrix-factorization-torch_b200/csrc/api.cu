@@ -191,11 +191,11 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
   const int words = mask_words_for(ncols), words_t = mask_words_for(nrows);
   const int rows_pad = cdiv(nrows, BM) * BM, cols_pad = cdiv(ncols, BM) * BM;
   {
-    mask_init_kernel<<<dim3(rows_pad, cdiv(words / 4, 128)), 128, 0, st>>>(mask, rows_pad, words, nrows, ncols);
+    mask_init_kernel<<<cdiv(static_cast<long long>(rows_pad) * (words / 4), 256), 256, 0, st>>>(mask, rows_pad, words, nrows, ncols);
     XB_LAUNCHED();
   }
   if (mask_t != nullptr) {
-    mask_init_kernel<<<dim3(cols_pad, cdiv(words_t / 4, 128)), 128, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
+    mask_init_kernel<<<cdiv(static_cast<long long>(cols_pad) * (words_t / 4), 256), 256, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
     XB_LAUNCHED();
   }
   const bool any_ids = (row_ids0 != nullptr) || (row_lists != nullptr && list_len > 0);
@@ -544,7 +544,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       for (int side = 0; side < 2; ++side) {
         p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
-        cand_finalize_kernel<<<cdiv(static_cast<long long>(B) * 32, 128), 128, 0, st>>>(
+        cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
             B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), MINE_CAP, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
         XB_LAUNCHED();
@@ -713,7 +713,7 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   p.topk_mining = 0;
   XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
-  cand_finalize_kernel<<<cdiv(static_cast<long long>(Q) * 32, 128), 128, 0, st>>>(
+  cand_finalize_kernel<<<cdiv(Q, 4), 128, 0, st>>>(
       Q, p.nR_pad, w.plan.nchunks * epi_parts(MODE_TOPK, 0, true), w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
   XB_LAUNCHED();
   float* stmp = reinterpret_cast<float*>(ws + w.scores);

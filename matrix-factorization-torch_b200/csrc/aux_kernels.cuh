@@ -111,10 +111,12 @@ __global__ void item_params_kernel(int N, const float* __restrict__ in2, const f
 // ------------------------------------------------------------------------------------------------
 __global__ void mask_init_kernel(uint32_t* __restrict__ mask, int rows_pad, int words, int rows_valid,
                                  int cols_valid) {
-  // grid = (rows_pad, ceil(words/4 / blockDim)); every thread writes one 16-byte group of a row
-  const int r = blockIdx.x;
-  const int g = blockIdx.y * blockDim.x + threadIdx.x;   // group of 4 words
-  if (g * 4 >= words) return;
+  // one thread per 16-byte group (4 words) of the bit matrix; 64-bit flat index, 32-bit divisions only
+  const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int gpr = words >> 2;                      // groups per row
+  if (gi >= static_cast<long long>(rows_pad) * gpr) return;
+  const int r = static_cast<int>(gi / gpr);
+  const int g = static_cast<int>(gi - static_cast<long long>(r) * gpr);
   uint4 v;
   if (r >= rows_valid) {
     v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -127,7 +129,7 @@ __global__ void mask_init_kernel(uint32_t* __restrict__ mask, int rows_pad, int 
     }
     v = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  *reinterpret_cast<uint4*>(mask + static_cast<size_t>(r) * words + g * 4) = v;
+  *reinterpret_cast<uint4*>(mask + gi * 4) = v;
 }
 
 __device__ __forceinline__ uint32_t hash64(long long id) {
@@ -448,38 +450,49 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
 // Candidate-list finalisation (top-k and mining): merge the per-chunk buffers of a row, sort by
 // (key desc, column asc) and emit the first k entries.  One warp per row; total entries <= 1024.
 // ------------------------------------------------------------------------------------------------
-__global__ void cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap, int k,
+constexpr int CANDF_STAGE = 1024;   // staging entries per warp (shared memory)
+__global__ void __launch_bounds__(128) cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap, int k,
                                      const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt,
                                      unsigned long long* __restrict__ out /*[nrows][out_stride], written at out_off*/,
                                      int out_stride, int out_off) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // One warp per row: the row's per-sub-chunk buffers are appended to a 1024-entry staging area in shared
+  // memory; whenever the next buffer would not fit, the staging area is reduced to its k largest entries with
+  // the same radix select the sweep uses.  The output is the (unordered) set of the k largest entries; callers
+  // rank it themselves.  k <= 512, cap <= 1024.
+  __shared__ unsigned long long stage[4][CANDF_STAGE];
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + wib;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  // Repeated fold: keep the running best (<= 512) in registers, fold in one chunk buffer (<= 512 used
-  // entries after its own compaction... a raw buffer may hold up to cap entries) at a time.
-  unsigned long long best[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) best[i] = 0ull;
-  // slots [0,16) of `best` hold the running top-512, slots [16,32) receive new entries
+  unsigned long long* st = stage[wib];
+  int cnt = 0;
   for (int c = 0; c < nchunks; ++c) {
     const size_t r = static_cast<size_t>(c) * nR_pad + row;
     const int n = cand_cnt[r];
+    if (n == 0) continue;
     const unsigned long long* buf = cand + r * cap;
-    for (int base = 0; base < n; base += 512) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int idx = base + i * 32 + lane;
-        best[16 + i] = idx < n ? buf[idx] : 0ull;
+    int done = 0;
+    while (done < n) {
+      if (cnt + min(n - done, 512) > CANDF_STAGE) {
+        __syncwarp();
+        compact_select<32>(st, cnt, k, lane);
+        cnt = min(cnt, k);
+        __syncwarp();
       }
-      warp_sort_desc<32>(best, lane);
+      const int take = min(n - done, CANDF_STAGE - cnt);
+      for (int i = lane; i < take; i += 32) st[cnt + i] = buf[done + i];
+      cnt += take;
+      done += take;
     }
   }
-  // element index of best[i] in lane l is i*32 + l
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < k) out[static_cast<size_t>(row) * out_stride + out_off + idx] = best[i];
+  __syncwarp();
+  if (cnt > k) {
+    compact_select<32>(st, cnt, k, lane);
+    cnt = k;
+    __syncwarp();
   }
+  for (int i = lane; i < k; i += 32)
+    out[static_cast<size_t>(row) * out_stride + out_off + i] = i < cnt ? st[i] : 0ull;
 }
 
 // entries -> (score, id) for retrieval in XB_COMPUTE_BF16 mode: score = exact fp32-accumulated dot of the

@@ -301,26 +301,88 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long (&e)[PER_LANE]
   }
 }
 
+// Warp-cooperative compaction of a row's candidate buffer: keep the `keep` largest of its `cnt` 64-bit
+// entries (unique: key << 32 | ~column), unordered, in buf[0, keep).  The keep-th largest entry is found by a
+// bit-wise binary search (64 rounds of "how many entries are >= candidate", counted across the warp); this is
+// ~10x less code and work than sorting the buffer, which matters because the compaction sits inside the
+// sweep's epilogue.  Returns the keep-th largest entry (the new admission threshold).
 template <int PER_LANE>
-__device__ __forceinline__ void compact_row(unsigned long long* buf, int cnt, int lane) {
+__device__ __forceinline__ unsigned long long compact_select(unsigned long long* buf, int cnt, int keep, int lane) {
   unsigned long long e[PER_LANE];
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) {
     const int idx = i * 32 + lane;
     e[i] = idx < cnt ? buf[idx] : 0ull;
   }
-  warp_sort_desc<PER_LANE>(e, lane);
+  auto warp_total = [](int c) {
 #pragma unroll
-  for (int i = 0; i < PER_LANE; ++i) buf[i * 32 + lane] = e[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+  };
+  // phase 1: the keep-th largest KEY (high word): largest T with count(key >= T) >= keep
+  uint32_t T = 0u;
+  int c_ge = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) c += (static_cast<uint32_t>(e[i] >> 32) >= cand) ? 1 : 0;
+    c = warp_total(c);
+    if (c >= keep) T = cand;
+  }
+  {
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) c += (static_cast<uint32_t>(e[i] >> 32) >= T) ? 1 : 0;
+    c_ge = warp_total(c);
+  }
+  unsigned long long thr = static_cast<unsigned long long>(T) << 32;
+  if (c_ge > keep) {
+    // ties on the key at the boundary: resolve on the low word (larger = lower column) among key == T
+    int c_gt = 0;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) c_gt += (static_cast<uint32_t>(e[i] >> 32) > T) ? 1 : 0;
+    c_gt = warp_total(c_gt);
+    uint32_t Lw = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = Lw | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i)
+        c += (static_cast<uint32_t>(e[i] >> 32) == T && static_cast<uint32_t>(e[i]) >= cand) ? 1 : 0;
+      c = warp_total(c);
+      if (c_gt + c >= keep) Lw = cand;
+    }
+    thr |= Lw;
+  }
+  // entries >= thr are exactly the `keep` largest (entries are unique); compact them to the front
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) mine += (e[i] >= thr && e[i] != 0ull) ? 1 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  int pos = incl - mine;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    if (e[i] >= thr && e[i] != 0ull) buf[pos++] = e[i];
+  }
+  return thr;
 }
 
-__device__ __forceinline__ void compact_dispatch(unsigned long long* buf, int cnt, int cap, int lane) {
+static __device__ __noinline__ unsigned long long compact_dispatch(unsigned long long* buf, int cnt, int cap, int keep, int lane) {
   switch (cap) {
-    case 64: compact_row<2>(buf, cnt, lane); break;
-    case 128: compact_row<4>(buf, cnt, lane); break;
-    case 256: compact_row<8>(buf, cnt, lane); break;
-    case 512: compact_row<16>(buf, cnt, lane); break;
-    default: compact_row<32>(buf, cnt, lane); break;
+    case 64: return compact_select<2>(buf, cnt, keep, lane);
+    case 128: return compact_select<4>(buf, cnt, keep, lane);
+    case 256: return compact_select<8>(buf, cnt, keep, lane);
+    case 512: return compact_select<16>(buf, cnt, keep, lane);
+    default: return compact_select<32>(buf, cnt, keep, lane);
   }
 }
 
@@ -328,6 +390,9 @@ __device__ __forceinline__ void compact_dispatch(unsigned long long* buf, int cn
 __device__ __forceinline__ uint32_t order_key(float f) {
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 // =================================================================================================
@@ -531,7 +596,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     float rg = 0.f, rgh = 0.f;                      // GRAD: row sums of G (all / hinge+logistic part)
     // TOPK state
     int cnt = 0;
-    uint32_t thr = row_ok ? 0u : 0xffffffffu;       // entries with key <= thr can no longer enter the top `keep`
+    uint32_t thr = row_ok ? 0u : 0xffffffffu;       // mining: entries with key <= thr can no longer enter the top `keep`
+    float thr_f = row_ok ? -INFINITY : INFINITY;    // retrieval: scores below thr_f can no longer enter
     unsigned long long* cbuf = nullptr;
     if (MODE == MODE_TOPK) cbuf = p.cand + out_row * p.cap;
 
@@ -539,7 +605,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
     constexpr int CSHARE = (CPAR + EP - 1) / EP;   // column-parameter floats this thread stages
     const int jl = e_tid & (BN - 1);
-    const bool use_cpar = (MODE == MODE_FWD || MODE == MODE_GRAD || MODE == MODE_TOPK) && p.cpar != nullptr;
+    const bool use_cpar = (MODE == MODE_FWD || MODE == MODE_GRAD) && p.cpar != nullptr;
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
       if (mrow != nullptr) {
@@ -576,7 +642,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const int j0 = (t_begin + t) * BN;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
-      if (t > 0) named_bar_sync(2, EPI_THREADS);
+      if (use_cpar && t > 0) named_bar_sync(2, EPI_THREADS);
       if (use_cpar) {
 #pragma unroll
         for (int u = 0; u < CSHARE; ++u) {
@@ -589,7 +655,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         fetch_mask(t_begin + t + 1, mw0_next, mw1_next);
         fetch_cpar(t_begin + t + 1, cpar_next);
       }
-      named_bar_sync(1, EPI_THREADS);
+      if (use_cpar) named_bar_sync(1, EPI_THREADS);
 
       mbar_wait(&bars->s_full[b], (t >> 1) & 1);
       tc_fence_after();
@@ -662,15 +728,41 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
           else store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_TOPK) {
-          // key per element (larger = better); masked / out-of-range columns get key 0
-          uint32_t key[32];
-          uint32_t kmax = 0;
+          // Streaming selection.  Retrieval compares raw scores with the row's float threshold: one fmax per
+          // element, and only a chunk that can beat the current k-th best takes the per-element path.
+          bool hit;
+          if (!p.topk_mining) {
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float S = __uint_as_float(v[c]);
-            uint32_t k;
-            if (p.topk_mining) {
-              const float2 ip = *reinterpret_cast<const float2*>(cpar_s + (ch * 32 + c) * 2);
+            for (int c = 4; c < 32; c += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[c]));
+              m1 = fmaxf(m1, __uint_as_float(v[c + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[c + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[c + 3]));
+            }
+            hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
+            if (hit) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float S = __uint_as_float(v[c]);
+                if (S >= thr_f && !((mwc >> c) & 1u)) {
+                  const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
+                  cbuf[cnt++] = (static_cast<unsigned long long>(max(order_key(S), 1u)) << 32) | static_cast<uint32_t>(~col);
+                }
+              }
+            }
+          } else {
+            // mining: key = bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by R asc);
+            // mode 2 mirrors the order (see mined_forward_kernel)
+            uint32_t key[32];
+            uint32_t kmax = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float S = __uint_as_float(v[c]);
+              // item parameters straight from global memory (one address per warp, L1 resident): the top-k
+              // epilogue has no per-tile barrier, so a compacting warp never stalls the others
+              const int jc = min(j0 + ch * 32 + c, p.nC - 1);
+              const float2 ip = __ldg(reinterpret_cast<const float2*>(p.cpar) + jc);
               float l2 = fmaf(rp_reg[0], S + ip.x, rp_reg[1]);
               if (LOGQ) l2 -= ip.y;
               float r = l2 + rp_reg[2];                        // rp_reg[2] = -L2_ii: R = L_ij - L_ii
@@ -679,26 +771,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               } else {
                 r += 0.0f;                                     // -0 -> +0 (losses.py:149 tests `< 0`)
               }
-              k = __float_as_uint(r) ^ 0x7fffffffu;           // semi-hard (R<0, desc) before hard (R>=0, asc)
+              uint32_t k = __float_as_uint(r) ^ 0x7fffffffu;
               k = (r != r) ? 1u : max(k, 1u);
-            } else {
-              k = (S != S) ? 1u : max(order_key(S), 1u);
+              k = ((mwc >> c) & 1u) ? 0u : k;
+              key[c] = k;
+              kmax = max(kmax, k);
             }
-            k = ((mwc >> c) & 1u) ? 0u : k;
-            key[c] = k;
-            kmax = max(kmax, k);
-          }
-          if (kmax > thr) {
+            hit = kmax > thr;
+            if (hit) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (key[c] > thr) {
-                const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
-                cbuf[cnt++] = (static_cast<unsigned long long>(key[c]) << 32) | static_cast<uint32_t>(~col);
+              for (int c = 0; c < 32; ++c) {
+                if (key[c] > thr) {
+                  const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
+                  cbuf[cnt++] = (static_cast<unsigned long long>(key[c]) << 32) | static_cast<uint32_t>(~col);
+                }
               }
             }
           }
-          // compaction: any row whose buffer cannot absorb another 32 candidates is sorted by its
-          // warp and truncated to the best `keep`; thr becomes the key of the last kept entry - 1.
+          // compaction: a row whose buffer cannot absorb another 32 candidates is reduced by its warp to the best
+          // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
+          // column wins ties).
           uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
           while (need) {
             const int src = __ffs(need) - 1;
@@ -706,13 +798,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
             const int n = __shfl_sync(0xffffffffu, cnt, src);
             __syncwarp();
-            compact_dispatch(buf, n, p.cap, lane);
+            const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane);
             __syncwarp();
-            const unsigned long long last = buf[p.keep - 1];
             if (lane == src) {
               cnt = p.keep;
-              const uint32_t kth = static_cast<uint32_t>(last >> 32);
-              thr = kth > 0 ? kth - 1 : 0;   // keys equal to the k-th stay eligible (lower column wins ties)
+              const uint32_t kk = static_cast<uint32_t>(kth >> 32);
+              thr = kk > 0 ? kk - 1 : 0;
+              thr_f = order_key_inv(kk);
             }
           }
         }
