@@ -161,6 +161,11 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
                     const void* rows, const void* cols, float* s_out, float* acc_out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* Debug hook: while `trace` (device, int64 [tiles][8]) is set, CTA (0,0) of every sweep writes SM clock stamps per
+ * tile: [0..2] MMA issuer before / after the S-buffer wait / after the operand wait, [3..5] epilogue warp before /
+ * after the score-tile wait / at the end of the tile, [6..7] TMA producer before / after the stage wait.  NULL = off. */
+int xb_debug_set_trace(int64_t* trace, int32_t tiles);
+
 /* Measurement hook (bench.py only): while enabled, every tensor-core sweep launch is
  * bracketed by CUDA events on its stream.  xb_sweep_timing(1) starts (and clears), xb_sweep_timing(0) stops;
  * xb_sweep_timing_read synchronises on the recorded events (the one entry point that blocks the host) and

@@ -89,6 +89,7 @@ SIGNATURES = {
     "xb_debug_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "xb_debug_scores": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xb_debug_loss_region": (_i32, [ctypes.POINTER(LossDesc), _i32, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "xb_debug_set_trace": (_i32, [_vp, _i32]),
     "xb_sweep_timing": (_i32, [_i32]),
     "xb_sweep_timing_read": (_i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "xb_last_error_string": (ctypes.c_char_p, []),

@@ -73,6 +73,10 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
     }                                                                                              \
   } while (0)
 
+// debug trace target (set by xb_debug_set_trace; nullptr = off)
+static std::atomic<long long*> g_trace{nullptr};
+static std::atomic<int> g_trace_tiles{0};
+
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -121,7 +125,7 @@ struct SweepPlan {
   bool ok;
 };
 
-static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int cpar_floats) {
+static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int cpar_floats, int topk_warps = 0) {
   SweepPlan pl{};
   pl.n_rblocks = cdiv(nR, BM);
   pl.n_ctiles = cdiv(nC, BN);
@@ -137,7 +141,7 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int c
   pl.nchunks = pl.n_ctiles > 0 ? cdiv(pl.n_ctiles, per) : 1;
   pl.ok = false;
   for (int ns = MAX_STAGES; ns >= (has_g ? 2 : 1); --ns) {
-    const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, has_g, cpar_floats);
+    const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, has_g, cpar_floats, topk_warps);
     if (lay.total <= SMEM_BUDGET) {
       pl.nstages = ns;
       pl.smem = lay.total;
@@ -240,7 +244,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->Kf = w->K + MINE_OVERFETCH;
   const int lm = sweep_lm_from_mask(d->loss_mask);
   const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
-  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, 2);
+  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 0, true) : 0);
   w->gq = plan_sweep(B, N, w->kp, w->parts, true, 2);
   w->gi = plan_sweep(N, B, w->kp, w->parts, true, gq_floats);
   size_t off = 0;
@@ -324,6 +328,8 @@ static SweepParams base_params(int nR, int nC, int kp, int parts, const SweepPla
   p.nstages = pl.nstages;
   p.tiles_per_cta = pl.tiles_per_cta;
   p.n_ctiles = pl.n_ctiles;
+  p.trace = g_trace.load();
+  p.trace_tiles = g_trace_tiles.load();
   return p;
 }
 
@@ -410,6 +416,12 @@ extern "C" {
 #pragma GCC visibility push(default)
 
 const char* xb_last_error_string(void) { return g_last_error.c_str(); }
+
+int xb_debug_set_trace(int64_t* trace, int32_t tiles) {
+  g_trace.store(reinterpret_cast<long long*>(trace));
+  g_trace_tiles.store(tiles);
+  return XB_OK;
+}
 
 int xb_sweep_timing(int32_t enable) {
   std::lock_guard<std::mutex> lk(g_timing_mutex);
@@ -635,7 +647,7 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   w->kfetch = d->k + (d->k < 32 ? 16 : 32);
   if (w->kfetch > d->num_items) w->kfetch = d->num_items > 0 ? d->num_items : 1;
   w->cap = topk_cap_for(w->kfetch);
-  w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, 2);
+  w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, 2, 4 * epi_parts(MODE_TOPK, 0, true));
   w->items_inplace = (d->in_dtype == XB_DTYPE_BF16 && w->parts == 1 && d->dim == w->kp);
   size_t off = 0;
   auto take = [&](size_t bytes) {

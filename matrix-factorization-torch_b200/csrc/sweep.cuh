@@ -74,13 +74,16 @@ struct SweepParams {
   int* cand_cnt;             // [EP*nchunks][nR_pad]
   int cap;                   // candidate buffer capacity per row (power of two, 64..1024)
   int keep;                  // entries kept by a compaction (<= cap/2)
+  long long* trace;          // debug: [tiles][8] clock64 stamps from CTA (0,0) (producer, MMA issuer, epilogue warp 2)
+  int trace_tiles;           // number of tiles traced (from tile 0 of the CTA)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
                              // 2: same with R negated (hard side first)
 };
 
 struct SweepSmemLayout {
-  uint32_t r_off, c_off, g_off, par_off, bar_off, total;
+  uint32_t r_off, c_off, g_off, par_off, bar_off, stage_off, total;
 };
+constexpr int TOPK_STAGE_STRIDE = 36;   // words per staged row (16-byte aligned, conflict-free 128-bit stores)
 
 // The gradient tile G is the A operand of the second MMA.  It lives in TMEM (columns after the accumulator,
 // double-buffered when kp <= 128) whenever 256 + kp + 64 <= 512 columns; only kp = 256 stages it in shared memory.
@@ -88,7 +91,7 @@ __host__ __device__ constexpr bool g_in_tmem(int kp) { return kp <= 192; }
 __host__ __device__ constexpr int g_tmem_bufs(int kp) { return kp <= 128 ? 2 : 1; }
 
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool has_g,
-                                                             int cpar_floats) {
+                                                             int cpar_floats, int topk_warps = 0) {
   SweepSmemLayout L;
   const uint32_t tile = static_cast<uint32_t>(kp / KBLK) * parts * BLOCK_BYTES;
   L.r_off = 0;
@@ -97,7 +100,8 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, 
   L.par_off = L.g_off + ((has_g && !g_in_tmem(kp)) ? 2u * BLOCK_BYTES : 0u);
   const uint32_t par_bytes = static_cast<uint32_t>(BN) * cpar_floats * 4u;  // column parameters of one tile
   L.bar_off = L.par_off + par_bytes;
-  L.total = L.bar_off + 256u;  // barriers + tmem pointer
+  L.stage_off = L.bar_off + 256u;  // barriers + tmem pointer
+  L.total = L.stage_off + static_cast<uint32_t>(topk_warps) * 32u * TOPK_STAGE_STRIDE * 4u;
   return L;
 }
 
@@ -106,8 +110,8 @@ struct SweepBars {
   uint64_t r_full;
   uint64_t c_full[MAX_STAGES];
   uint64_t c_empty[MAX_STAGES];
-  uint64_t s_full[2];
-  uint64_t s_empty[2];
+  uint64_t s_full[4];
+  uint64_t s_empty[4];
   uint64_t g_full[2];
   uint64_t g_empty[2];
   uint64_t acc_full;
@@ -404,18 +408,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
   constexpr int CPT = 4 / EP;                      // 32-column chunks per epilogue thread and tile
   constexpr int EPI_THREADS = 128 * EP;
+  // score-tile buffers in TMEM: without a gradient accumulator all 512 columns hold S tiles, so the MMA thread can
+  // run three tiles ahead of the epilogue and the per-tile barrier hand-shakes leave the critical path
+  constexpr int NSB = HAS_G ? 2 : 4;
   constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
   constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
 
   // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static smem here)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, HAS_G, CPAR);
+  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, HAS_G, CPAR, MODE == MODE_TOPK ? 4 * EP : 0);
   uint8_t* sR = smem + lay.r_off;
   uint8_t* sC = smem + lay.c_off;
   uint8_t* sG = smem + lay.g_off;
   float* sPar = reinterpret_cast<float*>(smem + lay.par_off);
   SweepBars* bars = reinterpret_cast<SweepBars*>(smem + lay.bar_off);
+  uint32_t* sStage = reinterpret_cast<uint32_t*>(smem + lay.stage_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -439,7 +447,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       mbar_init(&bars->c_full[s], 1);
       mbar_init(&bars->c_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&bars->s_full[b], 1);
       mbar_init(&bars->s_empty[b], EPI_THREADS);
     }
@@ -467,7 +475,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           tma_load_2d(sR + (pt * kb_n + kb) * BLOCK_BYTES, &tmR, &bars->r_full, pt * p.kp + kb * KBLK, rb * BM);
       for (int t = 0; t < T; ++t) {
         const int s = t % NS;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles;
+        if (tr) p.trace[t * 8 + 6] = clock64();
         mbar_wait(&bars->c_empty[s], ((t / NS) & 1) ^ 1);
+        if (tr) p.trace[t * 8 + 7] = clock64();
         mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes);
         uint8_t* dst = sC + static_cast<size_t>(s) * tile_bytes;
         for (int pt = 0; pt < p.parts; ++pt)
@@ -494,9 +505,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const uint32_t acc_tmem = tmem_base + TMEM_ACC_COL;
 
       auto issue_scores = [&](int t) {
-        const int b = t & 1, s = t % NS;
-        mbar_wait(&bars->s_empty[b], ((t >> 1) & 1) ^ 1);
+        const int b = t % NSB, s = t % NS;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && lane == 0;
+        if (tr) p.trace[t * 8 + 0] = clock64();
+        mbar_wait(&bars->s_empty[b], ((t / NSB) & 1) ^ 1);
+        if (tr) p.trace[t * 8 + 1] = clock64();
         mbar_wait(&bars->c_full[s], (t / NS) & 1);
+        if (tr) p.trace[t * 8 + 2] = clock64();
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b) * BN;
@@ -532,10 +547,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       };
 
       mbar_wait(&bars->r_full, 0);
+      if (!HAS_G) {
+        for (int t = 0; t < T; ++t) issue_scores(t);
+      } else {
       issue_scores(0);
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) issue_scores(t + 1);
-        if (HAS_G) {
+        {
           const int s = t % NS;
           const int gb = g_bufs == 2 ? (t & 1) : 0;
           mbar_wait(&bars->g_full[gb], (t / g_bufs) & 1);
@@ -571,8 +589,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           __syncwarp();
         }
       }
-      if (HAS_G && elect_one()) umma_commit(&bars->acc_full);
+      if (elect_one()) umma_commit(&bars->acc_full);
       __syncwarp();
+      }
     }
   } else if (T > 0) {
     // ======================================================================== epilogue warps
@@ -637,7 +656,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     fetch_cpar(t_begin, cpar_next);
 
     for (int t = 0; t < T; ++t) {
-      const int b = t & 1;
+      const int b = t % NSB;
       const int gb = g_bufs == 2 ? (t & 1) : 0;
       const int j0 = (t_begin + t) * BN;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
@@ -657,7 +676,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       }
       if (use_cpar) named_bar_sync(1, EPI_THREADS);
 
-      mbar_wait(&bars->s_full[b], (t >> 1) & 1);
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && warp == 2 && lane == 0;
+      if (tr) p.trace[t * 8 + 3] = clock64();
+      mbar_wait(&bars->s_full[b], (t / NSB) & 1);
+      if (tr) p.trace[t * 8 + 4] = clock64();
       tc_fence_after();
 
 #pragma unroll 1
@@ -728,8 +750,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
           else store_g_chunk(sG, row_l, ch * 32, pk);
         } else if (MODE == MODE_TOPK) {
-          // Streaming selection.  Retrieval compares raw scores with the row's float threshold: one fmax per
-          // element, and only a chunk that can beat the current k-th best takes the per-element path.
+          // Streaming selection.  Fast path: one fmax per element against the row's threshold.  A chunk in which
+          // some row can beat its current k-th best is staged in shared memory and each such row is then scanned by
+          // all 32 lanes at once (ballot + popc-compacted, coalesced appends) - rows hit rarely, warps hit often.
+          uint32_t w[32];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
           bool hit;
           if (!p.topk_mining) {
             float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
@@ -741,20 +765,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               m3 = fmaxf(m3, __uint_as_float(v[c + 3]));
             }
             hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
-            if (hit) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float S = __uint_as_float(v[c]);
-                if (S >= thr_f && !((mwc >> c) & 1u)) {
-                  const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
-                  cbuf[cnt++] = (static_cast<unsigned long long>(max(order_key(S), 1u)) << 32) | static_cast<uint32_t>(~col);
-                }
-              }
-            }
+            for (int c = 0; c < 32; ++c) w[c] = v[c];
           } else {
             // mining: key = bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by R asc);
             // mode 2 mirrors the order (see mined_forward_kernel)
-            uint32_t key[32];
             uint32_t kmax = 0;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -773,20 +788,47 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               }
               uint32_t k = __float_as_uint(r) ^ 0x7fffffffu;
               k = (r != r) ? 1u : max(k, 1u);
-              k = ((mwc >> c) & 1u) ? 0u : k;
-              key[c] = k;
+              w[c] = k;
               kmax = max(kmax, k);
             }
             hit = kmax > thr;
-            if (hit) {
+          }
+          uint32_t hm = __ballot_sync(0xffffffffu, hit);
+          if (hm) {
+            uint32_t* st = sStage + ((warp - 2) * 32) * TOPK_STAGE_STRIDE;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                if (key[c] > thr) {
-                  const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + c);
-                  cbuf[cnt++] = (static_cast<unsigned long long>(key[c]) << 32) | static_cast<uint32_t>(~col);
-                }
+            for (int q4 = 0; q4 < 8; ++q4)
+              *reinterpret_cast<uint4*>(st + lane * TOPK_STAGE_STRIDE + q4 * 4) =
+                  make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
+            __syncwarp();
+            const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + lane);
+            while (hm) {
+              const int src = __ffs(hm) - 1;
+              hm &= hm - 1;
+              const uint32_t x = st[src * TOPK_STAGE_STRIDE + lane];
+              const uint32_t m_src = __shfl_sync(0xffffffffu, mwc, src);
+              const int cnt_src = __shfl_sync(0xffffffffu, cnt, src);
+              bool pass;
+              uint32_t key;
+              if (!p.topk_mining) {
+                const float t_src = __shfl_sync(0xffffffffu, thr_f, src);
+                const float S = __uint_as_float(x);
+                pass = S >= t_src;
+                key = max(order_key(S), 1u);
+              } else {
+                const uint32_t t_src = __shfl_sync(0xffffffffu, thr, src);
+                pass = x > t_src;
+                key = x;
               }
+              pass = pass && !((m_src >> lane) & 1u);
+              const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+              if (pass) {
+                unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
+                buf[cnt_src + __popc(pm & ((1u << lane) - 1u))] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~col);
+              }
+              if (lane == src) cnt += __popc(pm);
             }
+            __syncwarp();
           }
           // compaction: a row whose buffer cannot absorb another 32 candidates is reduced by its warp to the best
           // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
@@ -812,6 +854,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       // accumulator buffer b fully read -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&bars->s_empty[b]);
+      if (tr) p.trace[t * 8 + 5] = clock64();
       if (HAS_G) {
         if (g_tmem) {
           tmem_st_wait();

@@ -4,7 +4,7 @@ sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import xfmr_b200
 from xfmr_b200 import _lib, synthetic
 dev = torch.device("cuda:0")
-Q, N = 128 * 148, 1_000_000
+Q, N = 128 * 148, 6_000_000
 items = synthetic.make_catalog(N, 128, seed=1, device=dev, dtype=torch.bfloat16)
 q = synthetic.make_catalog(Q, 128, seed=2, device=dev, dtype=torch.bfloat16)
 xfmr_b200.topk_search(q, items, 100); torch.cuda.synchronize()
