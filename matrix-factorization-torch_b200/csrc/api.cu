@@ -116,6 +116,21 @@ static int make_operand_map(CUtensorMap* map, const void* base, long long rows, 
   return XB_OK;
 }
 
+// norm blocks [rows, 32] bf16 (64-byte rows): box = 16 columns x 128 rows, 32-byte swizzle
+static int make_aug_map(CUtensorMap* map, const void* base, long long rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(XB_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {AUG_COLS, static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {AUG_COLS * 2};
+  cuuint32_t box[2] = {16, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(XB_ERR_CUDA, "cuTensorMapEncodeTiled (aug) failed with CUresult %d", static_cast<int>(r));
+  return XB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Launch plan of one sweep: how the column tiles are split across CTAs and how deep the TMA ring is.
 // ------------------------------------------------------------------------------------------------
@@ -125,7 +140,7 @@ struct SweepPlan {
   bool ok;
 };
 
-static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int cpar_floats, int topk_warps = 0) {
+static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool aug, int cpar_floats, int topk_warps = 0) {
   SweepPlan pl{};
   pl.n_rblocks = cdiv(nR, BM);
   pl.n_ctiles = cdiv(nC, BN);
@@ -141,7 +156,7 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, int c
   pl.nchunks = pl.n_ctiles > 0 ? cdiv(pl.n_ctiles, per) : 1;
   pl.ok = false;
   for (int ns = MAX_STAGES; ns >= (has_g ? 2 : 1); --ns) {
-    const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, has_g, cpar_floats, topk_warps);
+    const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, aug, cpar_floats, topk_warps);
     if (lay.total <= SMEM_BUDGET) {
       pl.nstages = ns;
       pl.smem = lay.total;
@@ -227,7 +242,7 @@ struct LossWs {
   int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
   bool mining;
   SweepPlan fwd, gq, gi;   // forward / mining sweep, dQ sweep, dI sweep
-  size_t qprep, iprep, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
+  size_t qprep, iprep, qaug, iaug, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
       ueff, qg, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
 
@@ -244,9 +259,9 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->Kf = w->K + MINE_OVERFETCH;
   const int lm = sweep_lm_from_mask(d->loss_mask);
   const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
-  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 0, true) : 0);
-  w->gq = plan_sweep(B, N, w->kp, w->parts, true, 2);
-  w->gi = plan_sweep(N, B, w->kp, w->parts, true, gq_floats);
+  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, true, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 0, true) : 0);
+  w->gq = plan_sweep(B, N, w->kp, w->parts, true, true, 2);
+  w->gi = plan_sweep(N, B, w->kp, w->parts, true, true, gq_floats);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -256,6 +271,8 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->qprep = take(rowb * B);
   w->iprep = take(rowb * N);
+  w->qaug = take(static_cast<size_t>(AUG_COLS) * 2 * B);
+  w->iaug = take(static_cast<size_t>(AUG_COLS) * 2 * N);
   w->qn2 = take(sizeof(float) * B);
   w->in2 = take(sizeof(float) * N);
   w->qfwd = take(sizeof(float4) * B);
@@ -311,9 +328,11 @@ static int check_loss_desc(const xb_loss_desc* d) {
 }
 
 template <typename T>
-static int prep_operand(const void* x, int n, int d, int kp, int parts, void* out, float* norm2, cudaStream_t st) {
+static int prep_operand(const void* x, int n, int d, int kp, int parts, void* out, float* norm2, void* aug,
+                        cudaStream_t st) {
   prep_operand_kernel<T><<<cdiv(static_cast<long long>(n) * 32, 256), 256, 0, st>>>(
-      static_cast<const T*>(x), n, d, kp, parts, static_cast<__nv_bfloat16*>(out), norm2);
+      static_cast<const T*>(x), n, d, kp, parts, static_cast<__nv_bfloat16*>(out), norm2,
+      static_cast<__nv_bfloat16*>(aug));
   XB_LAUNCHED();
   return XB_OK;
 }
@@ -368,31 +387,35 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     float* qg = reinterpret_cast<float*>(ws + w.qg);
     grad_params_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, lm, ueff, desc->sigma, qfwd, rowinfo, rowstat, qg);
     XB_LAUNCHED();
-    CUtensorMap tmQ, tmI;
+    CUtensorMap tmQ, tmI, tmQa, tmIa;
     if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
     if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
+    if ((rc = make_aug_map(&tmQa, ws + w.qaug, B))) return rc;
+    if ((rc = make_aug_map(&tmIa, ws + w.iaug, N))) return rc;
     {  // dQ sweep: rows = queries, columns = items
       SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
+      p.use_aug = 1;
       p.rpar = qg;
       p.cpar = reinterpret_cast<float*>(ws + w.ipar);
       p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
       p.mask_words = w.words;
       p.out_acc = accq;
       p.out_stats = rsq;
-      XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
+      XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
                                      w.gq.smem, st));
       nq = w.gq.nchunks;
       nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
     }
     {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
+      p.use_aug = 1;
       p.rpar = reinterpret_cast<float*>(ws + w.ipar);
       p.cpar = qg;
       p.mask = reinterpret_cast<uint32_t*>(ws + w.mask_t);
       p.mask_words = w.words_t;
       p.out_acc = acci;
       p.out_stats = rsi;
-      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
+      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, tmIa, tmQa, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
       ni_sub = ni * epi_parts(MODE_GRAD, lm, false);
@@ -501,11 +524,11 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
 
   // 1. operands -> bf16 (hi [, lo]) + norms
   if (desc->in_dtype == XB_DTYPE_F32) {
-    if ((rc = prep_operand<float>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), st))) return rc;
-    if ((rc = prep_operand<float>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), st))) return rc;
+    if ((rc = prep_operand<float>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), ws + w.qaug, st))) return rc;
+    if ((rc = prep_operand<float>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), ws + w.iaug, st))) return rc;
   } else {
-    if ((rc = prep_operand<__nv_bfloat16>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), st))) return rc;
-    if ((rc = prep_operand<__nv_bfloat16>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), ws + w.qaug, st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(item_embed, N, d, w.kp, w.parts, ws + w.iprep, reinterpret_cast<float*>(ws + w.in2), ws + w.iaug, st))) return rc;
   }
   // 2. per-row / per-column parameters of the logit map
   query_params_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
@@ -529,10 +552,13 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                          ws + w.pm_ws, st);
     if (rc != XB_OK) return rc;
     // 4. the sweep
-    CUtensorMap tmQ, tmI;
+    CUtensorMap tmQ, tmI, tmQa, tmIa;
     if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
     if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
+    if ((rc = make_aug_map(&tmQa, ws + w.qaug, B))) return rc;
+    if ((rc = make_aug_map(&tmIa, ws + w.iaug, N))) return rc;
     SweepParams p = base_params(B, N, w.kp, w.parts, w.fwd);
+    p.use_aug = 1;
     p.cpar = reinterpret_cast<float*>(ws + w.ipar);
     p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
     p.mask_words = w.words;
@@ -540,7 +566,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
     if (!w.mining) {
       p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
       p.out_stats = reinterpret_cast<float*>(ws + w.part);
-      XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
+      XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
       loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
                                                      reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
@@ -555,7 +581,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.keep = w.Kf;
       for (int side = 0; side < 2; ++side) {
         p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
-        XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, p, grid, w.fwd.smem, st));
+        XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
             B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), MINE_CAP, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
@@ -647,7 +673,7 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   w->kfetch = d->k + (d->k < 32 ? 16 : 32);
   if (w->kfetch > d->num_items) w->kfetch = d->num_items > 0 ? d->num_items : 1;
   w->cap = topk_cap_for(w->kfetch);
-  w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, 2, 4 * epi_parts(MODE_TOPK, 0, true));
+  w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, false, 2, 4 * epi_parts(MODE_TOPK, 0, true));
   w->items_inplace = (d->in_dtype == XB_DTYPE_BF16 && w->parts == 1 && d->dim == w->kp);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -702,13 +728,13 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
 
   const void* iprep = items;
   if (desc->in_dtype == XB_DTYPE_F32) {
-    if ((rc = prep_operand<float>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, st))) return rc;
-    if ((rc = prep_operand<float>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, nullptr, st))) return rc;
     iprep = ws + w.iprep;
   } else {
-    if ((rc = prep_operand<__nv_bfloat16>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(queries, Q, d, w.kp, w.parts, ws + w.qprep, nullptr, nullptr, st))) return rc;
     if (!w.items_inplace) {
-      if ((rc = prep_operand<__nv_bfloat16>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, st))) return rc;
+      if ((rc = prep_operand<__nv_bfloat16>(items, N, d, w.kp, w.parts, ws + w.iprep, nullptr, nullptr, st))) return rc;
       iprep = ws + w.iprep;
     }
   }
@@ -723,7 +749,7 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   p.cap = w.cap;
   p.keep = w.kfetch;
   p.topk_mining = 0;
-  XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
+  XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
   cand_finalize_kernel<<<cdiv(Q, 4), 128, 0, st>>>(
       Q, p.nR_pad, w.plan.nchunks * epi_parts(MODE_TOPK, 0, true), w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
@@ -821,7 +847,7 @@ struct DebugWs {
 bool debug_ws_layout(int nR, int nC, int dim, int compute, DebugWs* w) {
   w->kp = cdiv(dim, KBLK) * KBLK;
   w->parts = compute == XB_COMPUTE_SPLIT ? 2 : 1;
-  w->plan = plan_sweep(nR, nC, w->kp, w->parts, true, 2);
+  w->plan = plan_sweep(nR, nC, w->kp, w->parts, true, false, 2);
   // one chunk so that acc_out is the complete product
   w->plan.nchunks = 1;
   w->plan.tiles_per_cta = w->plan.n_ctiles;
@@ -854,11 +880,11 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int rc;
   if (in_dtype == XB_DTYPE_F32) {
-    if ((rc = prep_operand<float>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, st))) return rc;
-    if ((rc = prep_operand<float>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, nullptr, st))) return rc;
+    if ((rc = prep_operand<float>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, nullptr, st))) return rc;
   } else {
-    if ((rc = prep_operand<__nv_bfloat16>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, st))) return rc;
-    if ((rc = prep_operand<__nv_bfloat16>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(rows, num_rows, dim, w.kp, w.parts, ws + w.rprep, nullptr, nullptr, st))) return rc;
+    if ((rc = prep_operand<__nv_bfloat16>(cols, num_cols, dim, w.kp, w.parts, ws + w.cprep, nullptr, nullptr, st))) return rc;
   }
   CUtensorMap tmR, tmC;
   if ((rc = make_operand_map(&tmR, ws + w.rprep, num_rows, static_cast<long long>(w.parts) * w.kp))) return rc;
@@ -867,7 +893,7 @@ int xb_debug_scores(int32_t num_rows, int32_t num_cols, int32_t dim, int32_t in_
   p.dbg_s = s_out;
   p.out_acc = acc_out;
   p.out_stats = reinterpret_cast<float*>(ws + w.rs);
-  XB_SWEEP(launch_sweep_debug(tmR, tmC, p, dim3(1, w.plan.n_rblocks), w.plan.smem, st));
+  XB_SWEEP(launch_sweep_debug(tmR, tmC, tmR, tmC, p, dim3(1, w.plan.n_rblocks), w.plan.smem, st));
   return XB_OK;
 }
 

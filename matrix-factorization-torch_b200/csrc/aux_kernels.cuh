@@ -34,9 +34,14 @@ __device__ __forceinline__ float prepped_val(const __nv_bfloat16* row, int kp, i
 // Operand preparation: x [n, d] (fp32 or bf16) -> bf16 [n, parts * kp] (zero padded to kp, optional
 // hi/lo split) and the squared norm of the prepared values.  One warp per row.
 // ------------------------------------------------------------------------------------------------
+// `aug` (optional): the 32-column norm block of the row, h = -|x|^2/2 split into three bf16 terms:
+//   columns  0..15 (row role)    = {1, 1, 1, h_hi, h_mid, h_lo, 0...}
+//   columns 16..31 (column role) = {h_hi, h_mid, h_lo, 1, 1, 1, 0...}
+// so that <row role of r, column role of c> = h_r + h_c exactly as the tensor core sums it.
 template <typename T>
 __global__ void prep_operand_kernel(const T* __restrict__ x, int n, int d, int kp, int parts,
-                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2) {
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2,
+                                    __nv_bfloat16* __restrict__ aug) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -57,6 +62,19 @@ __global__ void prep_operand_kernel(const T* __restrict__ x, int n, int d, int k
   }
   acc = warp_sum(acc);
   if (lane == 0 && norm2 != nullptr) norm2[row] = acc;
+  if (aug != nullptr) {
+    const float h = -0.5f * acc;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(h);
+    const float r1 = h - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    const int k = lane & 15;
+    __nv_bfloat16 v;
+    if (lane < 16) v = k < 3 ? one : (k == 3 ? h0 : (k == 4 ? h1 : (k == 5 ? h2 : zero)));
+    else v = k == 0 ? h0 : (k == 1 ? h1 : (k == 2 ? h2 : (k < 6 ? one : zero)));
+    aug[static_cast<size_t>(row) * 32 + lane] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -90,7 +108,8 @@ __global__ void query_params_kernel(int B, int kp, int parts, const __nv_bfloat1
     const float lq2 = log_q != nullptr ? log_q[row] * LOG2E : 0.f;
     const float l2ii = a2 * dg - lq2;
     const float m2 = margin * LOG2E;
-    const float r2 = -0.5f * a2 * qn2[row];
+    const float r2 = 0.f;   // the norm terms ride in the contraction (aug K block): no per-row offset left
+    (void)qn2;
     qfwd[row] = make_float4(a2, r2, m2 - l2ii, s * m2);
     qmine[row] = make_float4(a2, r2, -l2ii, 0.f);
     rowinfo[row] = make_float4(s, w, t, l2ii);

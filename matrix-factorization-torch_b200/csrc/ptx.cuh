@@ -187,18 +187,19 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 // kernel, lo = (address >> 4) | (LBO >> 4) << 16 advances by plain 32-bit adds.  The issuing thread is on the
 // critical path of every tile (one thread feeds the tensor core), so nothing 64-bit is computed per MMA.
 constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t UMMA_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);     // 32-byte rows: SBO = 256 B, SWIZZLE_32B
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
 }
 __device__ __forceinline__ void umma_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                           uint32_t accumulate) {
+                                           uint32_t accumulate, uint32_t desc_hi = UMMA_DESC_HI_SW128) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
       "mov.b64 da, {%1, %3};\n\t"
       "mov.b64 db, {%2, %3};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(UMMA_DESC_HI_SW128), "r"(idesc), "r"(accumulate)
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
@@ -220,6 +221,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // ---------------------------------------------------------------- math helpers
 __device__ __forceinline__ float ex2f(float x) {
+#ifdef XB_NO_MUFU
+  return fmaf(x, x, 1.0f);   // timing experiment only
+#endif
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;

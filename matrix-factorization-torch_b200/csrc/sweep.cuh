@@ -4,6 +4,10 @@
 // double-buffered TMEM accumulator; four epilogue warps pull the tile out of TMEM with tcgen05.ld and
 // reduce it on the fly, so the B x N logit matrix of xfmr_rec/losses.py:9-12 never exists in HBM.
 //
+// Norm folding: for the losses the logit needs S_ij = q.v - (|q|^2 + |v|^2)/2 (losses.py:9-12).  Both norm terms ride
+// along as one extra 16-wide K block ("aug" operands: -|x|^2/2 as three bf16 terms against ones), so the tensor
+// core delivers S_ij itself and the epilogue spends a single FMA per logit.
+//
 //   MODE_FWD   epilogue = masked per-row loss statistics (count, relu sums, softplus sum, online
 //              logsumexp)                                         -> losses.py:164-246, 325-346
 //   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile in shared memory, followed by a second
@@ -31,9 +35,14 @@ constexpr int BM = 128;                  // tile rows  (UMMA M)
 constexpr int BN = 128;                  // tile cols  (UMMA N of the score MMA)
 constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
 constexpr int BLOCK_BYTES = 128 * 128;   // one [128 rows x 64 bf16] SWIZZLE_128B block
+constexpr int AUG_BYTES = 128 * 32;      // one [128 rows x 16 bf16] SWIZZLE_32B block (norm terms)
+constexpr int AUG_COLS = 32;             // aug row = 16 columns for the row role + 16 for the column role
 constexpr int MAX_EPI_PARTS = 4;           // epilogue warps come in EP sets of 4; set p owns tile columns [128p/EP, 128(p+1)/EP)
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TMEM_ACC_COL = 256;   // columns [256, 256+kp) hold the gradient accumulator
+// TMEM columns of the gradient kernels: S buffers | accumulator [kp] | G buffers (bf16 pairs, 64 columns each).
+// kp <= 192 double-buffers S; kp = 256 keeps a single S buffer so that accumulator and G still fit.
+__host__ __device__ constexpr int grad_s_bufs(int kp) { return kp <= 192 ? 2 : 1; }
+__host__ __device__ constexpr int grad_g_bufs(int kp) { return (512 - grad_s_bufs(kp) * 128 - kp) >= 128 ? 2 : 1; }
 constexpr int MAX_STAGES = 4;
 
 enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3 };
@@ -57,6 +66,7 @@ struct SweepParams {
   int kp;               // padded embedding dim, multiple of 64, <= 256
   int parts;            // 1 = bf16 operands; 2 = split (hi, lo) bf16 operands (fp32-grade scores)
   int nstages;          // column-tile ring depth
+  int use_aug;          // 1: operands carry the norm block (all loss sweeps); 0: plain dot products (retrieval)
   int tiles_per_cta;    // column tiles swept by one CTA
   int n_ctiles;         // ceil(nC / BN)
   // FWD : rpar = float4 per query {a2, r2, xoff, sm2};            cpar = float2 per item {c, lq2}
@@ -81,23 +91,19 @@ struct SweepParams {
 };
 
 struct SweepSmemLayout {
-  uint32_t r_off, c_off, g_off, par_off, bar_off, stage_off, total;
+  uint32_t r_off, c_off, ra_off, ca_off, par_off, bar_off, stage_off, total;
 };
 constexpr int TOPK_STAGE_STRIDE = 36;   // words per staged row (16-byte aligned, conflict-free 128-bit stores)
 
-// The gradient tile G is the A operand of the second MMA.  It lives in TMEM (columns after the accumulator,
-// double-buffered when kp <= 128) whenever 256 + kp + 64 <= 512 columns; only kp = 256 stages it in shared memory.
-__host__ __device__ constexpr bool g_in_tmem(int kp) { return kp <= 192; }
-__host__ __device__ constexpr int g_tmem_bufs(int kp) { return kp <= 128 ? 2 : 1; }
-
-__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool has_g,
+__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool aug,
                                                              int cpar_floats, int topk_warps = 0) {
   SweepSmemLayout L;
   const uint32_t tile = static_cast<uint32_t>(kp / KBLK) * parts * BLOCK_BYTES;
   L.r_off = 0;
   L.c_off = tile;
-  L.g_off = L.c_off + nstages * tile;
-  L.par_off = L.g_off + ((has_g && !g_in_tmem(kp)) ? 2u * BLOCK_BYTES : 0u);
+  L.ra_off = L.c_off + nstages * tile;                       // aug blocks: row operand, then one per stage
+  L.ca_off = L.ra_off + (aug ? AUG_BYTES : 0);
+  L.par_off = L.ca_off + (aug ? nstages * AUG_BYTES : 0);
   const uint32_t par_bytes = static_cast<uint32_t>(BN) * cpar_floats * 4u;  // column parameters of one tile
   L.bar_off = L.par_off + par_bytes;
   L.stage_off = L.bar_off + 256u;  // barriers + tmem pointer
@@ -141,14 +147,14 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
   // subtraction before exp2; `mref` is 0 until the row has seen a finite logit.
   const bool fresh = st.mx == NEG_BIG;
   const float mref = (LSE && !fresh) ? st.mx : 0.f;
-  const float off = qp.y - mref;
+  const float off = qp.y - mref;          // qp.y = 0 when the norms ride in the contraction
   float L[32];
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
-    const float4 cp = *reinterpret_cast<const float4*>(colp + c);  // {c0, lq0, c1, lq1}, warp-broadcast
-    float l0 = fmaf(qp.x, __uint_as_float(v[c]) + cp.x, off);
-    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]) + cp.z, off);
+    float l0 = fmaf(qp.x, __uint_as_float(v[c]), off);
+    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]), off);
     if (LOGQ) {
+      const float4 cp = *reinterpret_cast<const float4*>(colp + c);  // {-, lq0, -, lq1}, warp-broadcast
       l0 -= cp.y;
       l1 -= cp.w;
     }
@@ -159,6 +165,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
     L[c] = l0;
     L[c + 1] = l1;
   }
+  float ref = mref;   // what L is currently relative to
   if (LSE) {
     float m0 = fmaxf(L[0], L[4]), m1 = fmaxf(L[1], L[5]), m2 = fmaxf(L[2], L[6]), m3 = fmaxf(L[3], L[7]);
 #pragma unroll
@@ -168,28 +175,44 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
       m2 = fmaxf(m2, L[c + 2]);
       m3 = fmaxf(m3, L[c + 3]);
     }
-    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // relative to mref
-    if ((cm > 0.f || fresh) && cm > -INFINITY) {
-      // new running maximum: rebase this chunk and the accumulated sum
+    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // chunk maximum relative to mref
+    if (!fresh && cm <= 100.f) {
+      // common path: exponentials against the PREVIOUS running maximum, so they do not wait for this chunk's
+      // maximum (no serial phase: FMA, MUFU and FADD streams interleave); rescale afterwards if the maximum rose
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        s0 += ex2f(L[c]);
+        s1 += ex2f(L[c + 1]);
+        s2 += ex2f(L[c + 2]);
+        s3 += ex2f(L[c + 3]);
+      }
+      st.se += (s0 + s1) + (s2 + s3);
+      if (cm > 0.f) {
+        st.se *= ex2f(-cm);
+        st.mx = mref + cm;       // L stays relative to the old reference `ref`
+      }
+    } else if (cm > -INFINITY) {
+      // first finite chunk of the row, or a jump of the maximum too large for fp32: rebase, then sum
       const float nmx = mref + cm;
       st.se *= ex2f(st.mx - nmx);                            // fresh: ex2(-1e30 - x) = 0
       st.mx = nmx;
+      ref = nmx;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) L[c] -= cm;
+      for (int c = 0; c < 32; c += 4) {
+        L[c] -= cm; L[c + 1] -= cm; L[c + 2] -= cm; L[c + 3] -= cm;
+        s0 += ex2f(L[c]);
+        s1 += ex2f(L[c + 1]);
+        s2 += ex2f(L[c + 2]);
+        s3 += ex2f(L[c + 3]);
+      }
+      st.se += (s0 + s1) + (s2 + s3);
     }
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      s0 += ex2f(L[c]);
-      s1 += ex2f(L[c + 1]);
-      s2 += ex2f(L[c + 2]);
-      s3 += ex2f(L[c + 3]);
-    }
-    st.se += (s0 + s1) + (s2 + s3);
   }
   if (OTHER) {
     // the remaining losses need absolute logits: add the reference back (0 unless an LSE loss is also on)
-    const float back = LSE ? st.mx : 0.f;   // L is now relative to st.mx
+    const float back = LSE ? ref : 0.f;
     if (LM & LM_CONTR) {
       const float o = back + qp.w;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -230,9 +253,9 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
 // qp points at grad_qpar_floats(LM) floats: single {a2, off, k, 0}; all {a2, offC,kC, offI,kI, offM,kM,
 // offH,kH, offL,kL, 0}
 template <int LM, bool LOGQ>
-__device__ __forceinline__ void grad_elem(float S, float c_item, float lq2, const float* qp, float& g, float& h) {
+__device__ __forceinline__ void grad_elem(float S, float lq2, const float* qp, float& g, float& h) {
   // g = gradient of the non-pairwise losses, h = hinge + logistic part (needed separately for dL/dL_ii)
-  const float base = qp[0] * (S + c_item) - (LOGQ ? lq2 : 0.f);
+  const float base = LOGQ ? fmaf(qp[0], S, -lq2) : qp[0] * S;
   g = 0.f;
   h = 0.f;
   if (lm_single(LM)) {
@@ -247,19 +270,6 @@ __device__ __forceinline__ void grad_elem(float S, float c_item, float lq2, cons
     if (LM & LM_MINE) g += qp[6] * ex2f(base + qp[5]);
     if (LM & LM_HINGE) h += (base + qp[7]) > 0.f ? qp[8] : 0.f;
     if (LM & LM_LOGI) h += qp[10] * rcpf(1.f + ex2f(-(base + qp[9])));
-  }
-}
-
-// Writes 32 consecutive bf16 values of tile row `row` (columns col0 .. col0+31, col0 % 32 == 0) into the
-// K-major SWIZZLE_128B G tile: block = col / 64, 16-byte chunk index XOR (row & 7).
-__device__ __forceinline__ void store_g_chunk(uint8_t* sG, int row, int col0, const uint32_t (&pk)[16]) {
-  uint8_t* base = sG + (col0 >> 6) * BLOCK_BYTES + row * 128;
-  const int chunk0 = (col0 & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int chunk = (chunk0 + q) ^ (row & 7);
-    *reinterpret_cast<uint4*>(base + (chunk << 4)) =
-        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   }
 }
 
@@ -403,24 +413,26 @@ __device__ __forceinline__ float order_key_inv(uint32_t k) {
 template <int MODE, int LM, bool QROW, bool LOGQ>
 __global__ void __launch_bounds__(64 + 128 * epi_parts(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
-             const SweepParams p) {
+             const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmCa, const SweepParams p) {
   constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
   constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
   constexpr int CPT = 4 / EP;                      // 32-column chunks per epilogue thread and tile
   constexpr int EPI_THREADS = 128 * EP;
   // score-tile buffers in TMEM: without a gradient accumulator all 512 columns hold S tiles, so the MMA thread can
   // run three tiles ahead of the epilogue and the per-tile barrier hand-shakes leave the critical path
-  constexpr int NSB = HAS_G ? 2 : 4;
+  const int NSB = HAS_G ? grad_s_bufs(p.kp) : 4;
   constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
   constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
 
   // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static smem here)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, HAS_G, CPAR, MODE == MODE_TOPK ? 4 * EP : 0);
+  const bool aug = p.use_aug != 0;
+  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, aug, CPAR, MODE == MODE_TOPK ? 4 * EP : 0);
   uint8_t* sR = smem + lay.r_off;
   uint8_t* sC = smem + lay.c_off;
-  uint8_t* sG = smem + lay.g_off;
+  uint8_t* sRa = smem + lay.ra_off;
+  uint8_t* sCa = smem + lay.ca_off;
   float* sPar = reinterpret_cast<float*>(smem + lay.par_off);
   SweepBars* bars = reinterpret_cast<SweepBars*>(smem + lay.bar_off);
   uint32_t* sStage = reinterpret_cast<uint32_t*>(smem + lay.stage_off);
@@ -431,9 +443,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const int nblk = kb_n * p.parts;
   const uint32_t tile_bytes = static_cast<uint32_t>(nblk) * BLOCK_BYTES;
   const int NS = p.nstages;
-  const bool g_tmem = HAS_G && g_in_tmem(p.kp);
-  const int g_bufs = g_tmem ? g_tmem_bufs(p.kp) : 1;
-  const uint32_t g_col0 = TMEM_ACC_COL + static_cast<uint32_t>(p.kp);   // TMEM columns of the G buffers
+  const int g_bufs = grad_g_bufs(p.kp);
+  const uint32_t acc_col = static_cast<uint32_t>(grad_s_bufs(p.kp)) * BN;   // TMEM columns of the gradient accumulator
+  const uint32_t g_col0 = acc_col + static_cast<uint32_t>(p.kp);          // ... and of the G buffers
 
   const int chunk = blockIdx.x;
   const int rb = blockIdx.y;
@@ -459,6 +471,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     fence_barrier_init();
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmC);
+    if (aug) {
+      tma_prefetch_desc(&tmRa);
+      tma_prefetch_desc(&tmCa);
+    }
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before();
@@ -469,22 +485,25 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   if (warp == 0) {
     // ======================================================================== TMA producer
     if (lane == 0 && T > 0) {
-      mbar_arrive_expect_tx(&bars->r_full, tile_bytes);
+      const uint32_t aug_bytes = aug ? AUG_BYTES : 0u;
+      mbar_arrive_expect_tx(&bars->r_full, tile_bytes + aug_bytes);
       for (int pt = 0; pt < p.parts; ++pt)
         for (int kb = 0; kb < kb_n; ++kb)
           tma_load_2d(sR + (pt * kb_n + kb) * BLOCK_BYTES, &tmR, &bars->r_full, pt * p.kp + kb * KBLK, rb * BM);
+      if (aug) tma_load_2d(sRa, &tmRa, &bars->r_full, 0, rb * BM);              // row-role columns [0,16)
       for (int t = 0; t < T; ++t) {
         const int s = t % NS;
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles;
         if (tr) p.trace[t * 8 + 6] = clock64();
         mbar_wait(&bars->c_empty[s], ((t / NS) & 1) ^ 1);
         if (tr) p.trace[t * 8 + 7] = clock64();
-        mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes);
+        mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes + aug_bytes);
         uint8_t* dst = sC + static_cast<size_t>(s) * tile_bytes;
         for (int pt = 0; pt < p.parts; ++pt)
           for (int kb = 0; kb < kb_n; ++kb)
             tma_load_2d(dst + (pt * kb_n + kb) * BLOCK_BYTES, &tmC, &bars->c_full[s], pt * p.kp + kb * KBLK,
                         (t_begin + t) * BN);
+        if (aug) tma_load_2d(sCa + s * AUG_BYTES, &tmCa, &bars->c_full[s], 16, (t_begin + t) * BN);   // column role
       }
     }
   } else if (warp == 1) {
@@ -498,11 +517,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const uint32_t r_lo = umma_desc_lo(smem_u32(sR), 16);                       // K-major operand tiles
       const uint32_t c_lo0 = umma_desc_lo(smem_u32(sC), 16);
       const uint32_t cmn_lo0 = umma_desc_lo(smem_u32(sC), BLOCK_BYTES);           // same tiles read MN-major
-      const uint32_t g_lo = umma_desc_lo(smem_u32(sG), 16);
+      const uint32_t ra_lo = umma_desc_lo(smem_u32(sRa), 16);                     // norm blocks (SWIZZLE_32B rows)
+      const uint32_t ca_lo0 = umma_desc_lo(smem_u32(sCa), 16);
       const uint32_t tile_lo = tile_bytes >> 4;                                   // descriptor units are 16 B
       const uint32_t blk_lo = BLOCK_BYTES >> 4;
       const uint32_t part_lo = static_cast<uint32_t>(kb_n) * blk_lo;
-      const uint32_t acc_tmem = tmem_base + TMEM_ACC_COL;
+      const uint32_t acc_tmem = tmem_base + acc_col;
 
       auto issue_scores = [&](int t) {
         const int b = t % NSB, s = t % NS;
@@ -540,6 +560,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               }
             }
           }
+          // + (-|r|^2/2 - |c|^2/2): one K=16 step over the norm blocks
+          if (aug) umma_ss_lo(d_tmem, ra_lo, ca_lo0 + static_cast<uint32_t>(s) * (AUG_BYTES >> 4), idesc_s, 1u, UMMA_DESC_HI_SW32);
           umma_commit(&bars->s_full[b]);
           if (!HAS_G) umma_commit(&bars->c_empty[s]);
         }
@@ -563,24 +585,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             // (N = embedding dim, K = tile row; 16 rows = 2048 B), hi part then lo part in split mode.
             const uint32_t b_lo = cmn_lo0 + static_cast<uint32_t>(s) * tile_lo;
             uint32_t acc = t != 0 ? 1u : 0u;
-            if (g_tmem) {
-              const uint32_t a_tmem = tmem_base + g_col0 + static_cast<uint32_t>(gb * 64);   // 8 columns per K-step
-              for (int pt = 0; pt < p.parts; ++pt) {
+            const uint32_t a_tmem = tmem_base + g_col0 + static_cast<uint32_t>(gb * 64);   // 8 columns per K-step
+            for (int pt = 0; pt < p.parts; ++pt) {
 #pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk) {
-                  umma_ts_lo(acc_tmem, a_tmem + kk * 8, b_lo + pt * part_lo + kk * 128, idesc_g, acc);
-                  acc = 1;
-                }
-              }
-            } else {
-              for (int pt = 0; pt < p.parts; ++pt) {
-#pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk) {
-                  // A = G tile in shared memory, K-major: block kk/4, 32 B per K-step inside the block
-                  umma_ss_lo(acc_tmem, g_lo + (kk >> 2) * blk_lo + (kk & 3) * 2, b_lo + pt * part_lo + kk * 128, idesc_g,
-                             acc);
-                  acc = 1;
-                }
+              for (int kk = 0; kk < BN / 16; ++kk) {
+                umma_ts_lo(acc_tmem, a_tmem + kk * 8, b_lo + pt * part_lo + kk * 128, idesc_g, acc);
+                acc = 1;
               }
             }
             umma_commit(&bars->g_empty[gb]);
@@ -624,7 +634,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
     constexpr int CSHARE = (CPAR + EP - 1) / EP;   // column-parameter floats this thread stages
     const int jl = e_tid & (BN - 1);
-    const bool use_cpar = (MODE == MODE_FWD || MODE == MODE_GRAD) && p.cpar != nullptr;
+    // staged column parameters: the item side only carries the LogQ term now (the norms ride in the contraction);
+    // the query-side gradient blocks of the item-major sweep are always staged
+    const bool use_cpar = p.cpar != nullptr && ((MODE == MODE_FWD && LOGQ) || (MODE == MODE_GRAD && (LOGQ || !QROW)));
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
       if (mrow != nullptr) {
@@ -706,8 +718,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               const float S = __uint_as_float(v[c + u]);
               float gv, hv;
               if (QROW) {
-                const float2 ip = *reinterpret_cast<const float2*>(cpar_s + col * 2);
-                grad_elem<LM, LOGQ>(S, ip.x, ip.y, rp_reg, gv, hv);
+                float lq2 = 0.f;
+                if (LOGQ) lq2 = cpar_s[col * 2 + 1];
+                grad_elem<LM, LOGQ>(S, lq2, rp_reg, gv, hv);
               } else {
                 float qp[grad_qpar_floats(LM)];
                 const float4* q4 = reinterpret_cast<const float4*>(cpar_s + col * CPAR);
@@ -716,7 +729,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                   const float4 x = q4[i];
                   qp[4 * i] = x.x; qp[4 * i + 1] = x.y; qp[4 * i + 2] = x.z; qp[4 * i + 3] = x.w;
                 }
-                grad_elem<LM, LOGQ>(S, rp_reg[0], rp_reg[1], qp, gv, hv);
+                grad_elem<LM, LOGQ>(S, rp_reg[1], qp, gv, hv);
               }
               const bool masked = (mwc >> (c + u)) & 1u;
               hv = masked ? 0.f : hv;
@@ -729,8 +742,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
           // the G buffer must have been consumed by its previous second MMA before it is overwritten
           if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
-          if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
-          else store_g_chunk(sG, row_l, ch * 32, pk);
+          tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
         } else if (MODE == MODE_DEBUG) {
           uint32_t pk[16];
 #pragma unroll
@@ -747,8 +759,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             pk[c >> 1] = pack_bf16x2(a, bb);
           }
           if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
-          if (g_tmem) tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
-          else store_g_chunk(sG, row_l, ch * 32, pk);
+          tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
         } else if (MODE == MODE_TOPK) {
           // Streaming selection.  Fast path: one fmax per element against the row's threshold.  A chunk in which
           // some row can beat its current k-th best is staged in shared memory and each such row is then scanned by
@@ -774,12 +785,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float S = __uint_as_float(v[c]);
-              // item parameters straight from global memory (one address per warp, L1 resident): the top-k
-              // epilogue has no per-tile barrier, so a compacting warp never stalls the others
-              const int jc = min(j0 + ch * 32 + c, p.nC - 1);
-              const float2 ip = __ldg(reinterpret_cast<const float2*>(p.cpar) + jc);
-              float l2 = fmaf(rp_reg[0], S + ip.x, rp_reg[1]);
-              if (LOGQ) l2 -= ip.y;
+              // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
+              //  per-tile barrier, so a compacting warp never stalls the others)
+              float l2 = rp_reg[0] * S;                         // norms ride in the contraction
+              if (LOGQ) {
+                const int jc = min(j0 + ch * 32 + c, p.nC - 1);
+                l2 -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+              }
               float r = l2 + rp_reg[2];                        // rp_reg[2] = -L2_ii: R = L_ij - L_ii
               if (p.topk_mining == 2) {
                 r = (r == 0.f) ? -0.0f : -r;                   // mirrored order; an exact 0 belongs to BOTH first groups
@@ -856,12 +868,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       mbar_arrive(&bars->s_empty[b]);
       if (tr) p.trace[t * 8 + 5] = clock64();
       if (HAS_G) {
-        if (g_tmem) {
-          tmem_st_wait();
-          tc_fence_before();
-        } else {
-          fence_proxy_async_smem();
-        }
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(&bars->g_full[gb]);
       }
     }
@@ -878,7 +886,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
       for (int cc = part; cc < p.kp / 32; cc += EP) {   // accumulator chunks are dealt round-robin to the parts
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + TMEM_ACC_COL + static_cast<uint32_t>(cc * 32), v);
+        tmem_ld32(tmem_base + lane_off + acc_col + static_cast<uint32_t>(cc * 32), v);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; c += 4)

@@ -2,9 +2,9 @@
 namespace xb {
 #define XB_FWD_CASE(LMV)                                                                                   \
   case LMV:                                                                                                \
-    return logq ? launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, true>, MODE_FWD, LMV, true, tmR, tmC, p, grid, smem, st)  \
-                : launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, false>, MODE_FWD, LMV, true, tmR, tmC, p, grid, smem, st);
-cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+    return logq ? launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, true>, MODE_FWD, LMV, true, tmR, tmC, tmRa, tmCa, p, grid, smem, st)  \
+                : launch_sweep_impl(sweep_kernel<MODE_FWD, LMV, true, false>, MODE_FWD, LMV, true, tmR, tmC, tmRa, tmCa, p, grid, smem, st);
+cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                              const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   switch (lm) {
     XB_FWD_CASE(LM_CONTR)

@@ -2,9 +2,9 @@
 namespace xb {
 #define XB_GRAD_CASE(LMV)                                                                                     \
   case LMV:                                                                                                   \
-    return logq ? launch_sweep_impl(sweep_kernel<MODE_GRAD, LMV, true, true>, MODE_GRAD, LMV, true, tmR, tmC, p, grid, smem, st)     \
-                : launch_sweep_impl(sweep_kernel<MODE_GRAD, LMV, true, false>, MODE_GRAD, LMV, true, tmR, tmC, p, grid, smem, st);
-cudaError_t launch_sweep_grad_qrow(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+    return logq ? launch_sweep_impl(sweep_kernel<MODE_GRAD, LMV, true, true>, MODE_GRAD, LMV, true, tmR, tmC, tmRa, tmCa, p, grid, smem, st)     \
+                : launch_sweep_impl(sweep_kernel<MODE_GRAD, LMV, true, false>, MODE_GRAD, LMV, true, tmR, tmC, tmRa, tmCa, p, grid, smem, st);
+cudaError_t launch_sweep_grad_qrow(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                                    const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   switch (lm) {
     XB_GRAD_CASE(LM_CONTR)

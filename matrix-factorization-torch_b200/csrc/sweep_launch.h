@@ -7,23 +7,23 @@
 #include "sweep.cuh"
 
 namespace xb {
-cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                              const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
-cudaError_t launch_sweep_grad_qrow(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+cudaError_t launch_sweep_grad_qrow(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                                    const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
-cudaError_t launch_sweep_grad_qcol(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC,
+cudaError_t launch_sweep_grad_qcol(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                                    const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
-cudaError_t launch_sweep_topk(bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const SweepParams& p,
+cudaError_t launch_sweep_topk(bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa, const SweepParams& p,
                               dim3 grid, size_t smem, cudaStream_t st);
-cudaError_t launch_sweep_debug(const CUtensorMap& tmR, const CUtensorMap& tmC, const SweepParams& p, dim3 grid,
+cudaError_t launch_sweep_debug(const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa, const SweepParams& p, dim3 grid,
                                size_t smem, cudaStream_t st);
 
 template <typename K>
-inline cudaError_t launch_sweep_impl(K kernel, int mode, int lm, bool qrow, const CUtensorMap& tmR, const CUtensorMap& tmC,
+inline cudaError_t launch_sweep_impl(K kernel, int mode, int lm, bool qrow, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                                      const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kernel<<<grid, 64 + 128 * epi_parts(mode, lm, qrow), smem, st>>>(tmR, tmC, p);
+  kernel<<<grid, 64 + 128 * epi_parts(mode, lm, qrow), smem, st>>>(tmR, tmC, tmRa, tmCa, p);
   return cudaGetLastError();
 }
 }  // namespace xb

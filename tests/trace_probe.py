@@ -26,3 +26,17 @@ _lib.lib.xb_debug_set_trace(trace.data_ptr(), NT)
 xfmr_b200.topk_search(q, items, 100); torch.cuda.synchronize()
 _lib.lib.xb_debug_set_trace(None, 0)
 show("TOPK", 3000, 3012)
+
+# loss sweeps at config 2
+inp = bench.make_c2(dev, 0, torch.bfloat16)
+m = xfmr_b200.InfomationNoiseContrastiveEstimationLoss(sigma=5.0, margin=0.5)
+q2 = inp["user_embed"].detach().requires_grad_(True); v2 = inp["item_embed"].detach().requires_grad_(True)
+loss = m(q2, v2, inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"]); torch.cuda.synchronize()
+trace.zero_()
+_lib.lib.xb_debug_set_trace(trace.data_ptr(), 77)
+loss = m(q2, v2, inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"]); torch.cuda.synchronize()
+show("FWD InfoNCE", 40, 52)
+trace.zero_()
+loss.backward(); torch.cuda.synchronize()
+_lib.lib.xb_debug_set_trace(None, 0)
+show("GRAD dI (item-major)", 16, 28)
