@@ -243,7 +243,7 @@ struct LossWs {
   bool mining;
   SweepPlan fwd, gq, gi;   // forward / mining sweep, dQ sweep, dI sweep
   size_t qprep, iprep, qaug, iaug, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
-      ueff, qg, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
+      ueff, qg, qs, qaugb, csign, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
 
 static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
@@ -289,6 +289,10 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->ueff = take(sizeof(float) * 8);
   w->redpart = take(sizeof(double) * XB_NUM_LOSSES * cdiv(B, LOSS_RED_ROWS));
   w->qg = take(sizeof(float) * 12 * B);
+  // operands of the item-major sweep with the per-query factors folded in (grad_fold_kernel)
+  w->qs = take(rowb * B);
+  w->qaugb = take(static_cast<size_t>(AUG_COLS) * 2 * B);
+  w->csign = take(sizeof(uint32_t) * (cdiv(B, 32) + 4));
   const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
   w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
   w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * MAX_EPI_PARTS * w->B_pad);
@@ -415,7 +419,30 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       p.mask_words = w.words_t;
       p.out_acc = acci;
       p.out_stats = rsi;
-      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, tmQ, tmIa, tmQa, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
+      const CUtensorMap* tmQc = &tmQ;
+      const CUtensorMap* tmQca = &tmQa;
+      CUtensorMap tmQs, tmQab;
+      if (grad_expfast(lm)) {
+        // exponential loss: fold sign, offset and magnitude of every query into the streamed operand and its aug
+        // block, so the epilogue of the item-major sweep needs no per-column parameters
+        float cabs = fabsf(desc->sigma) * 1.4426950408889634f;
+        if (!(cabs > 0.f)) cabs = 1.f;
+        uint32_t* csign = reinterpret_cast<uint32_t*>(ws + w.csign);
+        if (cudaMemsetAsync(csign, 0, sizeof(uint32_t) * (cdiv(B, 32) + 4), st) != cudaSuccess)
+          return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
+        grad_fold_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+            B, w.kp, w.parts, qprep, reinterpret_cast<const float*>(ws + w.qn2), qg, cabs,
+            reinterpret_cast<__nv_bfloat16*>(ws + w.qs), reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), csign);
+        XB_LAUNCHED();
+        if ((rc = make_operand_map(&tmQs, ws + w.qs, B, static_cast<long long>(w.parts) * w.kp))) return rc;
+        if ((rc = make_aug_map(&tmQab, ws + w.qaugb, B))) return rc;
+        tmQc = &tmQs;
+        tmQca = &tmQab;
+        p.cabs = cabs;
+        p.gsign_src = ueff + (lm == LM_INFONCE ? XB_LOSS_INFONCE : XB_LOSS_MINE);
+        p.csign = csign;
+      }
+      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, *tmQc, tmIa, *tmQca, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
       ni_sub = ni * epi_parts(MODE_GRAD, lm, false);

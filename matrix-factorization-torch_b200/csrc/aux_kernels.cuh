@@ -345,6 +345,50 @@ __global__ void grad_params_kernel(int B, int lm, const float* __restrict__ u, f
   }
 }
 
+// Operand folding for the item-major gradient sweep of an exponential loss (InfoNCE / MINE, single-loss call).
+// There the tile is rows = items, columns = queries, and G_ij = k_j 2^(a2_j S_ij + off_j [- lq2_i]) with per-QUERY
+// factors.  With c = |sigma| log2 e and s'_j = sign(a2_j):  a2_j S_ij + off_j + log2|k_j| = c (s'_j S_ij + o_j),
+// o_j = (off_j + log2|k_j|) / c.  The tensor core delivers T_ij = s'_j S_ij + o_j directly when
+//   * the streamed operand is qs_j = s'_j q_j (exact in bf16), and
+//   * the column role of its aug block is {t0, t1, t2, s', s', s'} with t = s'_j (-|q_j|^2/2) + o_j in three bf16
+//     terms (the row role of the items stays {1, 1, 1, h0, h1, h2}).
+// The second MMA multiplies |G| by the same sign-folded tile, so sign(k_j) = s'_j sign(u) is applied by the operand and
+// a global sign(u) on the way out.  Queries without a gradient (k = 0, target 0, empty rows) fold to all-zero
+// operands and o = -300 / c, i.e. |G| = 0.  csign bit j = [s'_j < 0] (needed for the row sums of G only).
+__global__ void grad_fold_kernel(int B, int kp, int parts, const __nv_bfloat16* __restrict__ qprep,
+                                 const float* __restrict__ qn2, const float* __restrict__ qg, float cabs,
+                                 __nv_bfloat16* __restrict__ qs, __nv_bfloat16* __restrict__ qaug,
+                                 uint32_t* __restrict__ csign) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float4 g = reinterpret_cast<const float4*>(qg)[row];   // {a2, off, k, 0}
+  const bool live = g.z != 0.f && fabsf(g.z) <= 3.0e38f && fabsf(g.y) <= 3.0e38f && g.x != 0.f;
+  const float sg = !live ? 0.f : (g.x > 0.f ? 1.f : -1.f);
+  const int rowlen = parts * kp;   // multiple of 64
+  const uint4* src = reinterpret_cast<const uint4*>(qprep + static_cast<size_t>(row) * rowlen);
+  uint4* dst = reinterpret_cast<uint4*>(qs + static_cast<size_t>(row) * rowlen);
+  const uint32_t flip = sg < 0.f ? 0x80008000u : 0u;
+  for (int k = lane; k < rowlen / 8; k += 32) {
+    uint4 x = src[k];
+    if (sg == 0.f) x = make_uint4(0u, 0u, 0u, 0u);
+    else { x.x ^= flip; x.y ^= flip; x.z ^= flip; x.w ^= flip; }
+    dst[k] = x;
+  }
+  const float o = live ? (g.y + log2f(fabsf(g.z))) / cabs : -300.f / cabs;
+  const float t = sg * (-0.5f * qn2[row]) + o;
+  const __nv_bfloat16 t0 = __float2bfloat16_rn(t);
+  const float r1 = t - __bfloat162float(t0);
+  const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
+  const __nv_bfloat16 sb = __float2bfloat16_rn(sg), zero = __float2bfloat16_rn(0.f);
+  const int k = lane & 15;
+  __nv_bfloat16 v = zero;
+  if (lane >= 16) v = k == 0 ? t0 : (k == 1 ? t1 : (k == 2 ? t2 : (k < 6 ? sb : zero)));
+  qaug[static_cast<size_t>(row) * 32 + lane] = v;
+  if (lane == 0 && sg < 0.f) atomicOr(csign + (row >> 5), 1u << (row & 31));
+}
+
 template <typename T>
 __device__ __forceinline__ void store_out(T* p, float v);
 template <>

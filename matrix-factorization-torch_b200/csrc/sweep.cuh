@@ -1,8 +1,8 @@
 // The score-tile "sweep" kernel: one CTA keeps a 128-row tile of the ROW operand resident in shared
 // memory and streams 128-row tiles of the COLUMN operand past it with TMA.  Each (row tile, column tile)
-// pair is one 128x128 score tile S = R . C^T computed by tcgen05.mma (bf16 in, fp32 accumulate) into a
-// double-buffered TMEM accumulator; four epilogue warps pull the tile out of TMEM with tcgen05.ld and
-// reduce it on the fly, so the B x N logit matrix of xfmr_rec/losses.py:9-12 never exists in HBM.
+// pair is one 128x128 score tile S = R . C^T computed by tcgen05.mma (bf16 in, fp32 accumulate) into TMEM;
+// the epilogue warps pull the tile out of TMEM with tcgen05.ld and reduce it on the fly, so the B x N logit
+// matrix of xfmr_rec/losses.py:9-12 never exists in HBM.
 //
 // Norm folding: for the losses the logit needs S_ij = q.v - (|q|^2 + |v|^2)/2 (losses.py:9-12).  Both norm terms ride
 // along as one extra 16-wide K block ("aug" operands: -|x|^2/2 as three bf16 terms against ones), so the tensor
@@ -10,17 +10,20 @@
 //
 //   MODE_FWD   epilogue = masked per-row loss statistics (count, relu sums, softplus sum, online
 //              logsumexp)                                         -> losses.py:164-246, 325-346
-//   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile in shared memory, followed by a second
-//              tcgen05.mma  acc[128 x d] += G[128 x 128] . C_tile[128 x d]  (flash-style recompute).
-//              With (R,C) = (Q,I) acc is dQ; with (R,C) = (I,Q) the same kernel yields dI.
+//   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile written back into TMEM (over the score tile it came
+//              from), followed by a second tcgen05.mma  acc[128 x d] += G[128 x 128] . C_tile[128 x d]
+//              (flash-style recompute).  With (R,C) = (Q,I) acc is dQ; with (R,C) = (I,Q) the same kernel yields dI.
 //   MODE_TOPK  epilogue = streaming per-row top-k selection (retrieval, and the semi-hard negative
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then 4*EP epilogue warps:
-// thread <-> (TMEM lane = tile row, column part).  EP = 4 (16 epilogue warps, one 32-column chunk each) for the
-// single-loss forward / gradient variants, EP = 2 where register pressure is high (all-losses variants, top-k).
-// The epilogue is latency-bound (tcgen05.ld, MUFU, dependent FP chains), so warps per sub-partition matter.
+// thread <-> (TMEM lane = tile row, column part).  EP = 4 (16 epilogue warps) for the single-loss forward / gradient
+// variants, EP = 2 where register pressure is high (all-losses variants, top-k).
+//
+// Epilogue pipeline: a thread walks its columns in UNITS of 16 (32 for top-k).  The tcgen05.ld of unit u+1 is issued
+// before the math of unit u, so TMEM latency hides behind the MUFU / FMA work; a score buffer is handed back to the
+// MMA warp as soon as its last unit sits in registers.  Barrier arrivals are one elected lane per warp.
 // Per-row outputs are written per "sub-chunk" = EP * column chunk + column part and merged by the finalisers.
 #pragma once
 #include <cuda.h>
@@ -39,10 +42,10 @@ constexpr int AUG_BYTES = 128 * 32;      // one [128 rows x 16 bf16] SWIZZLE_32B
 constexpr int AUG_COLS = 32;             // aug row = 16 columns for the row role + 16 for the column role
 constexpr int MAX_EPI_PARTS = 4;           // epilogue warps come in EP sets of 4; set p owns tile columns [128p/EP, 128(p+1)/EP)
 constexpr uint32_t TMEM_COLS = 512;
-// TMEM columns of the gradient kernels: S buffers | accumulator [kp] | G buffers (bf16 pairs, 64 columns each).
-// kp <= 192 double-buffers S; kp = 256 keeps a single S buffer so that accumulator and G still fit.
-__host__ __device__ constexpr int grad_s_bufs(int kp) { return kp <= 192 ? 2 : 1; }
-__host__ __device__ constexpr int grad_g_bufs(int kp) { return (512 - grad_s_bufs(kp) * 128 - kp) >= 128 ? 2 : 1; }
+// TMEM columns of the gradient kernels: NB score buffers of 128 columns | accumulator [kp].  The bf16 gradient tile
+// G overwrites the score tile it was computed from (unit of 16 score columns -> 8 packed columns at the same
+// offset), so a buffer is S, then G, then free again once its second MMA has been issued.
+__host__ __device__ constexpr int grad_bufs(int kp) { return (512 - kp) / 128 >= 3 ? 3 : 2; }
 constexpr int MAX_STAGES = 4;
 
 enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3 };
@@ -52,9 +55,12 @@ enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 
 
 __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
 // number of epilogue column parts of a kernel variant
-__host__ __device__ constexpr int epi_parts(int mode, int lm, bool qrow) {
-  return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/) && qrow && lm != 0 && lm_single(lm)) ? 4 : 2;
+__host__ __device__ constexpr int epi_parts(int mode, int lm, bool /*qrow*/) {
+  return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
 }
+// single-loss gradient kernels of the exponential losses take the lean path: |G| = 2^x, signs and per-row /
+// per-column factors folded into offsets, operands and the final write-out
+__host__ __device__ constexpr bool grad_expfast(int lm) { return lm_single(lm) && (lm & (2 | 4)) != 0; }
 // floats of per-query gradient parameters: single loss {a2, off, k, 0}; all {a2, (off,k) x 5, 0}
 __host__ __device__ constexpr int grad_qpar_floats(int lm) { return lm_single(lm) ? 4 : 12; }
 
@@ -88,6 +94,11 @@ struct SweepParams {
   int trace_tiles;           // number of tiles traced (from tile 0 of the CTA)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
                              // 2: same with R negated (hard side first)
+  // GRAD, item-major sweep of an exponential loss (see grad_fold_kernel): the column operand is the sign-folded
+  // query tile and its aug block carries the per-query offset, so x_ij = cabs * T_ij - lq2_i and |G_ij| = 2^x_ij
+  float cabs;                // |sigma| * log2(e)
+  const float* gsign_src;    // upstream gradient scalar; its sign multiplies the accumulator on the way out
+  const uint32_t* csign;     // bit j set <=> column (query) j enters with a negative sign (row sums of G only)
 };
 
 struct SweepSmemLayout {
@@ -117,9 +128,8 @@ struct SweepBars {
   uint64_t c_full[MAX_STAGES];
   uint64_t c_empty[MAX_STAGES];
   uint64_t s_full[4];
-  uint64_t s_empty[4];
-  uint64_t g_full[2];
-  uint64_t g_empty[2];
+  uint64_t s_empty[4];   // FWD / TOPK: epilogue -> MMA (one arrival per epilogue warp)
+  uint64_t g_full[4];    // GRAD: G tile written (one arrival per epilogue warp)
   uint64_t acc_full;
   uint32_t tmem_base;
 };
@@ -138,86 +148,70 @@ struct FwdState {
   float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
 };
 
+// One unit = 16 consecutive score columns of one row.  `s` holds the raw scores, bit c of m16 masks column c.
+// LSE losses: the exponentials are taken against the row's running REFERENCE st.mx (set by the first finite unit and
+// moved only when a sum would leave the safe fp32 range), so the common path is FFMA2 -> MUFU -> FADD2 with no
+// maximum and no dependent chain; (st.mx, st.se) pairs merge exactly in loss_rows_kernel whatever the reference is.
 template <int LM, bool LOGQ, bool MASKED>
-__device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, const float4 qp,
-                                          const float2* __restrict__ colp, FwdState<LM>& st) {
+__device__ __forceinline__ void fwd_unit(const uint32_t (&s)[16], uint32_t m16, const float4 qp,
+                                         const float2* __restrict__ colp, FwdState<LM>& st) {
   constexpr bool LSE = (LM & (LM_INFONCE | LM_MINE)) != 0;
   constexpr bool OTHER = (LM & ~(LM_INFONCE | LM_MINE)) != 0;
-  // Logits are formed RELATIVE to the running maximum (L - mref) so that the common case needs no
-  // subtraction before exp2; `mref` is 0 until the row has seen a finite logit.
   const bool fresh = st.mx == NEG_BIG;
   const float mref = (LSE && !fresh) ? st.mx : 0.f;
   const float off = qp.y - mref;          // qp.y = 0 when the norms ride in the contraction
-  float L[32];
+  float L[16];
 #pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    float l0 = fmaf(qp.x, __uint_as_float(v[c]), off);
-    float l1 = fmaf(qp.x, __uint_as_float(v[c + 1]), off);
+  for (int c = 0; c < 16; c += 2) {
+    float2 l = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), make_float2(qp.x, qp.x),
+                     make_float2(off, off));
     if (LOGQ) {
       const float4 cp = *reinterpret_cast<const float4*>(colp + c);  // {-, lq0, -, lq1}, warp-broadcast
-      l0 -= cp.y;
-      l1 -= cp.w;
+      l.x -= cp.y;
+      l.y -= cp.w;
     }
     if (MASKED) {
-      l0 = ((mw >> c) & 1u) ? -INFINITY : l0;
-      l1 = ((mw >> (c + 1)) & 1u) ? -INFINITY : l1;
+      l.x = ((m16 >> c) & 1u) ? -INFINITY : l.x;
+      l.y = ((m16 >> (c + 1)) & 1u) ? -INFINITY : l.y;
     }
-    L[c] = l0;
-    L[c + 1] = l1;
+    L[c] = l.x;
+    L[c + 1] = l.y;
   }
-  float ref = mref;   // what L is currently relative to
   if (LSE) {
-    float m0 = fmaxf(L[0], L[4]), m1 = fmaxf(L[1], L[5]), m2 = fmaxf(L[2], L[6]), m3 = fmaxf(L[3], L[7]);
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 8; c < 32; c += 4) {
-      m0 = fmaxf(m0, L[c]);
-      m1 = fmaxf(m1, L[c + 1]);
-      m2 = fmaxf(m2, L[c + 2]);
-      m3 = fmaxf(m3, L[c + 3]);
+    for (int c = 0; c < 16; c += 4) {
+      a0 = fadd2(a0, make_float2(ex2f(L[c]), ex2f(L[c + 1])));
+      a1 = fadd2(a1, make_float2(ex2f(L[c + 2]), ex2f(L[c + 3])));
     }
-    const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // chunk maximum relative to mref
-    if (!fresh && cm <= 100.f) {
-      // common path: exponentials against the PREVIOUS running maximum, so they do not wait for this chunk's
-      // maximum (no serial phase: FMA, MUFU and FADD streams interleave); rescale afterwards if the maximum rose
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float t = (a0.x + a0.y) + (a1.x + a1.y);
+    if (!fresh && t <= 1.0e12f) {
+      st.se += t;
+    } else {
+      // first finite unit of the row, or values far above the reference (also inf / NaN sums): move the reference to
+      // this unit's maximum and redo the unit against it
+      float cm = L[0];
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        s0 += ex2f(L[c]);
-        s1 += ex2f(L[c + 1]);
-        s2 += ex2f(L[c + 2]);
-        s3 += ex2f(L[c + 3]);
-      }
-      st.se += (s0 + s1) + (s2 + s3);
-      if (cm > 0.f) {
-        st.se *= ex2f(-cm);
-        st.mx = mref + cm;       // L stays relative to the old reference `ref`
-      }
-    } else if (cm > -INFINITY) {
-      // first finite chunk of the row, or a jump of the maximum too large for fp32: rebase, then sum
-      const float nmx = mref + cm;
-      st.se *= ex2f(st.mx - nmx);                            // fresh: ex2(-1e30 - x) = 0
-      st.mx = nmx;
-      ref = nmx;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int c = 1; c < 16; ++c) cm = fmaxf(cm, L[c]);
+      if (cm > -INFINITY) {
+        const float nmx = mref + cm;
+        st.se *= ex2f(st.mx - nmx);                            // fresh: ex2(-1e30 - x) = 0
+        st.mx = nmx;
+        float r = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        L[c] -= cm; L[c + 1] -= cm; L[c + 2] -= cm; L[c + 3] -= cm;
-        s0 += ex2f(L[c]);
-        s1 += ex2f(L[c + 1]);
-        s2 += ex2f(L[c + 2]);
-        s3 += ex2f(L[c + 3]);
+        for (int c = 0; c < 16; ++c) r += ex2f(L[c] - cm);
+        st.se += r;
       }
-      st.se += (s0 + s1) + (s2 + s3);
     }
   }
   if (OTHER) {
     // the remaining losses need absolute logits: add the reference back (0 unless an LSE loss is also on)
-    const float back = LSE ? ref : 0.f;
+    const float back = LSE ? mref : 0.f;
     if (LM & LM_CONTR) {
       const float o = back + qp.w;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
+      for (int c = 0; c < 16; c += 4) {
         s0 += fmaxf(L[c] + o, 0.f);
         s1 += fmaxf(L[c + 1] + o, 0.f);
         s2 += fmaxf(L[c + 2] + o, 0.f);
@@ -229,7 +223,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
       const float o = back + qp.z;
       float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
+      for (int c = 0; c < 16; c += 2) {
         const float x0 = L[c] + o, x1 = L[c + 1] + o;
         if (LM & LM_HINGE) {
           h0 += fmaxf(x0, 0.f);
@@ -245,7 +239,31 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&v)[32], uint32_t mw, 
       st.lsum += g0 + g1;
     }
   }
-  st.cnt += static_cast<float>(32 - __popc(mw));
+  st.cnt += static_cast<float>(16 - __popc(m16));
+}
+
+// Lean gradient unit of the exponential losses: |G| = 2^(xa * S + xo [- lq2_col]), masked columns -> 0, row sum in
+// `rs` (packed pair), bf16 pairs in pk.  `lqp` (LogQ, query-major sweep only) = float2 per column {-, lq2} in smem.
+template <bool LOGQ_COL, bool MASKED>
+__device__ __forceinline__ void grad_fast_unit(const uint32_t (&s)[16], uint32_t m16, float xa, float xo,
+                                               const float2* __restrict__ lqp, float2& rs, uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    float2 x = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), make_float2(xa, xa),
+                     make_float2(xo, xo));
+    if (LOGQ_COL) {
+      const float4 cp = *reinterpret_cast<const float4*>(lqp + c);
+      x.x -= cp.y;
+      x.y -= cp.w;
+    }
+    float e0 = ex2f(x.x), e1 = ex2f(x.y);
+    if (MASKED) {
+      e0 = ((m16 >> c) & 1u) ? 0.f : e0;
+      e1 = ((m16 >> (c + 1)) & 1u) ? 0.f : e1;
+    }
+    rs = fadd2(rs, make_float2(e0, e1));
+    pk[c >> 1] = pack_bf16x2(e0, e1);
+  }
 }
 
 // Gradient element: g = sum_l k_l * phi_l(a2 * (S + c) + off_l - lq2)
@@ -410,17 +428,33 @@ __device__ __forceinline__ float order_key_inv(uint32_t k) {
 }
 
 // =================================================================================================
+template <int UW>
+__device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&v)[UW]) {
+  if constexpr (UW == 16) tmem_ld16(taddr, v);
+  else tmem_ld32(taddr, v);
+}
+template <int UW>
+__device__ __forceinline__ void tmem_ld_wait_unit(uint32_t (&v)[UW]) {
+  if constexpr (UW == 16) tmem_ld_wait16(v);
+  else tmem_ld_wait32(v);
+}
+
 template <int MODE, int LM, bool QROW, bool LOGQ>
 __global__ void __launch_bounds__(64 + 128 * epi_parts(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
              const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmCa, const SweepParams p) {
   constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
   constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
-  constexpr int CPT = 4 / EP;                      // 32-column chunks per epilogue thread and tile
+  constexpr int PW = BN / EP;                            // tile columns owned by one epilogue thread
+  constexpr int UW = (MODE == MODE_TOPK) ? 32 : 16;      // columns per unit
+  constexpr int UPT = PW / UW;                           // units per thread and tile
+  constexpr int EPI_WARPS = 4 * EP;
   constexpr int EPI_THREADS = 128 * EP;
+  constexpr bool EXPFAST = (MODE == MODE_GRAD) && grad_expfast(LM);
+  constexpr bool FOLDED = EXPFAST && !QROW;              // column operand = sign-folded queries (grad_fold_kernel)
   // score-tile buffers in TMEM: without a gradient accumulator all 512 columns hold S tiles, so the MMA thread can
   // run three tiles ahead of the epilogue and the per-tile barrier hand-shakes leave the critical path
-  const int NSB = HAS_G ? grad_s_bufs(p.kp) : 4;
+  const int NSB = HAS_G ? grad_bufs(p.kp) : 4;
   constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
   constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
 
@@ -443,9 +477,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const int nblk = kb_n * p.parts;
   const uint32_t tile_bytes = static_cast<uint32_t>(nblk) * BLOCK_BYTES;
   const int NS = p.nstages;
-  const int g_bufs = grad_g_bufs(p.kp);
-  const uint32_t acc_col = static_cast<uint32_t>(grad_s_bufs(p.kp)) * BN;   // TMEM columns of the gradient accumulator
-  const uint32_t g_col0 = acc_col + static_cast<uint32_t>(p.kp);          // ... and of the G buffers
+  const uint32_t acc_col = static_cast<uint32_t>(grad_bufs(p.kp)) * BN;   // TMEM columns of the gradient accumulator
 
   const int chunk = blockIdx.x;
   const int rb = blockIdx.y;
@@ -461,11 +493,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(&bars->s_full[b], 1);
-      mbar_init(&bars->s_empty[b], EPI_THREADS);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars->g_full[b], EPI_THREADS);
-      mbar_init(&bars->g_empty[b], 1);
+      mbar_init(&bars->s_empty[b], EPI_WARPS);
+      mbar_init(&bars->g_full[b], EPI_WARPS);
     }
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
@@ -528,7 +557,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         const int b = t % NSB, s = t % NS;
         const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && lane == 0;
         if (tr) p.trace[t * 8 + 0] = clock64();
-        mbar_wait(&bars->s_empty[b], ((t / NSB) & 1) ^ 1);
+        // FWD / TOPK: the epilogue hands the buffer back.  GRAD: buffer b last held tile t - NSB, whose second MMA
+        // this thread has already issued - tcgen05.mma of one thread execute in issue order, so no barrier is needed.
+        if (!HAS_G) mbar_wait(&bars->s_empty[b], ((t / NSB) & 1) ^ 1);
         if (tr) p.trace[t * 8 + 1] = clock64();
         mbar_wait(&bars->c_full[s], (t / NS) & 1);
         if (tr) p.trace[t * 8 + 2] = clock64();
@@ -572,35 +603,37 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if (!HAS_G) {
         for (int t = 0; t < T; ++t) issue_scores(t);
       } else {
-      issue_scores(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_scores(t + 1);
-        {
+        // score tiles run AHEAD tiles in front of the second MMA: G(t) is being computed by the epilogue while the
+        // tensor core already holds S(t+1) .. S(t+AHEAD), so neither side waits for the other in steady state
+        int ahead = NSB - 1;
+        if (ahead > NS - 1) ahead = NS - 1;
+        for (int t = 0; t < ahead && t < T; ++t) issue_scores(t);
+        for (int t = 0; t < T; ++t) {
+          if (t + ahead < T) issue_scores(t + ahead);
           const int s = t % NS;
-          const int gb = g_bufs == 2 ? (t & 1) : 0;
-          mbar_wait(&bars->g_full[gb], (t / g_bufs) & 1);
+          const int b = t % NSB;
+          mbar_wait(&bars->g_full[b], (t / NSB) & 1);
           tc_fence_after();
           if (elect_one()) {
-            // acc[128 x kp] += G[128 x 128] . C_tile[128 x kp]: B = the column-operand tile read MN-major
-            // (N = embedding dim, K = tile row; 16 rows = 2048 B), hi part then lo part in split mode.
+            // acc[128 x kp] += G[128 x 128] . C_tile[128 x kp]: A = G from TMEM (K-step kk = 8 packed columns at
+            // buffer + 16 kk), B = the column-operand tile read MN-major (N = embedding dim, K = tile row; 16 rows =
+            // 2048 B), hi part then lo part in split mode.
             const uint32_t b_lo = cmn_lo0 + static_cast<uint32_t>(s) * tile_lo;
             uint32_t acc = t != 0 ? 1u : 0u;
-            const uint32_t a_tmem = tmem_base + g_col0 + static_cast<uint32_t>(gb * 64);   // 8 columns per K-step
+            const uint32_t a_tmem = tmem_base + static_cast<uint32_t>(b) * BN;
             for (int pt = 0; pt < p.parts; ++pt) {
 #pragma unroll
               for (int kk = 0; kk < BN / 16; ++kk) {
-                umma_ts_lo(acc_tmem, a_tmem + kk * 8, b_lo + pt * part_lo + kk * 128, idesc_g, acc);
+                umma_ts_lo(acc_tmem, a_tmem + kk * 16, b_lo + pt * part_lo + kk * 128, idesc_g, acc);
                 acc = 1;
               }
             }
-            umma_commit(&bars->g_empty[gb]);
             umma_commit(&bars->c_empty[s]);
           }
           __syncwarp();
         }
-      }
-      if (elect_one()) umma_commit(&bars->acc_full);
-      __syncwarp();
+        if (elect_one()) umma_commit(&bars->acc_full);
+        __syncwarp();
       }
     }
   } else if (T > 0) {
@@ -608,39 +641,57 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int part = (warp - 2) >> 2;               // column part of the tile this warp reduces
     const int row_l = quad * 32 + lane;             // tile row == TMEM lane
-    const int e_tid = threadIdx.x - 64;             // 0..255, used for cooperative parameter loads
+    const int e_tid = threadIdx.x - 64;             // 0..EPI_THREADS-1, used for cooperative parameter loads
     const int row = rb * BM + row_l;
     const bool row_ok = row < p.nR;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const size_t out_row = static_cast<size_t>(chunk * EP + part) * p.nR_pad + row;
+    const uint32_t part_col = static_cast<uint32_t>(part * PW);
 
     float rp_reg[RPAR];
 #pragma unroll
     for (int i = 0; i < RPAR; ++i)
       rp_reg[i] = (row_ok && p.rpar != nullptr) ? p.rpar[static_cast<size_t>(row) * RPAR + i] : 0.f;
 
+    // lean exponential-gradient path: x = xa * S + xo, result scaled by oscale on the way out
+    float xa = 0.f, xo = -300.f, oscale = 1.f;
+    if (EXPFAST) {
+      if (QROW) {
+        const float k = rp_reg[2];
+        const bool live = k != 0.f && fabsf(k) <= 3.0e38f && fabsf(rp_reg[1]) <= 3.0e38f;
+        xa = live ? rp_reg[0] : 0.f;
+        xo = live ? rp_reg[1] + log2f(fabsf(k)) : -300.f;
+        oscale = k < 0.f ? -1.f : 1.f;
+      } else {
+        xa = p.cabs;
+        xo = LOGQ ? -rp_reg[1] : 0.f;
+        oscale = (p.gsign_src != nullptr && *p.gsign_src < 0.f) ? -1.f : 1.f;
+      }
+    }
+
     const uint32_t* mrow = (p.mask != nullptr) ? p.mask + static_cast<size_t>(row) * p.mask_words : nullptr;
 
     FwdState<LM> st;
-    float rg = 0.f, rgh = 0.f;                      // GRAD: row sums of G (all / hinge+logistic part)
+    float2 rs2 = make_float2(0.f, 0.f);             // GRAD lean path: packed row sum of |G|
+    float rneg = 0.f;                               //   ... part of it that belongs to negative-sign columns
+    float rg = 0.f, rgh = 0.f;                      // GRAD generic path: row sums of G (all / hinge+logistic part)
     // TOPK state
     int cnt = 0;
     uint32_t thr = row_ok ? 0u : 0xffffffffu;       // mining: entries with key <= thr can no longer enter the top `keep`
     float thr_f = row_ok ? -INFINITY : INFINITY;    // retrieval: scores below thr_f can no longer enter
-    unsigned long long* cbuf = nullptr;
-    if (MODE == MODE_TOPK) cbuf = p.cand + out_row * p.cap;
 
     // Per-tile side inputs (mask words of this row, parameters of the tile's columns) come from global
     // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
     constexpr int CSHARE = (CPAR + EP - 1) / EP;   // column-parameter floats this thread stages
     const int jl = e_tid & (BN - 1);
-    // staged column parameters: the item side only carries the LogQ term now (the norms ride in the contraction);
-    // the query-side gradient blocks of the item-major sweep are always staged
-    const bool use_cpar = p.cpar != nullptr && ((MODE == MODE_FWD && LOGQ) || (MODE == MODE_GRAD && (LOGQ || !QROW)));
+    // staged column parameters: the item side only carries the LogQ term (the norms ride in the contraction); the
+    // query-side gradient blocks of the item-major sweep are staged unless the lean path folded them away
+    const bool use_cpar = p.cpar != nullptr &&
+                          ((MODE == MODE_FWD && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED))));
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
       if (mrow != nullptr) {
-        if (CPT == 2) {
+        if (PW == 64) {
           const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (jt >> 5) + 2 * part);
           m0 = m2.x;
           m1 = m2.y;
@@ -649,7 +700,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           m1 = 0u;
         }
       } else {  // no mask given: only the column bound applies
-        const int rem0 = p.nC - (jt + 32 * CPT * part), rem1 = rem0 - 32;
+        const int rem0 = p.nC - (jt + PW * part), rem1 = rem0 - 32;
         m0 = rem0 >= 32 ? 0u : (rem0 <= 0 ? 0xffffffffu : (0xffffffffu << rem0));
         m1 = rem1 >= 32 ? 0u : (rem1 <= 0 ? 0xffffffffu : (0xffffffffu << rem1));
       }
@@ -662,15 +713,31 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         cv[u] = (use_cpar && i < CPAR && j < p.nC) ? p.cpar[static_cast<size_t>(j) * CPAR + i] : 0.f;
       }
     };
-    uint32_t mw0_next = 0u, mw1_next = 0u;
+    auto fetch_sign = [&](int tile, uint32_t& s0, uint32_t& s1) {
+      s0 = 0u;
+      s1 = 0u;
+      if (FOLDED && p.csign != nullptr) {
+        const int w = (tile * BN + PW * part) >> 5;
+        s0 = __ldg(p.csign + w);
+        if (PW == 64) s1 = __ldg(p.csign + w + 1);
+      }
+    };
+    uint32_t mw0_next = 0u, mw1_next = 0u, sg0_next = 0u, sg1_next = 0u;
     float cpar_next[CSHARE];
     fetch_mask(t_begin, mw0_next, mw1_next);
     fetch_cpar(t_begin, cpar_next);
+    fetch_sign(t_begin, sg0_next, sg1_next);
+
+    // first unit of the first tile
+    uint32_t v[UW];
+    mbar_wait(&bars->s_full[0], 0);
+    tc_fence_after();
+    tmem_ld_unit<UW>(tmem_base + lane_off + part_col, v);
 
     for (int t = 0; t < T; ++t) {
       const int b = t % NSB;
-      const int gb = g_bufs == 2 ? (t & 1) : 0;
       const int j0 = (t_begin + t) * BN;
+      const uint32_t buf_addr = tmem_base + lane_off + static_cast<uint32_t>(b * BN) + part_col;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
       if (use_cpar && t > 0) named_bar_sync(2, EPI_THREADS);
@@ -681,41 +748,85 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           if (i < CPAR) cpar_s[jl * CPAR + i] = cpar_next[u];
         }
       }
-      const uint32_t mw0 = mw0_next, mw1 = mw1_next;
+      const uint32_t mw0 = mw0_next, mw1 = mw1_next, sg0 = sg0_next, sg1 = sg1_next;
       if (t + 1 < T) {
         fetch_mask(t_begin + t + 1, mw0_next, mw1_next);
         fetch_cpar(t_begin + t + 1, cpar_next);
+        fetch_sign(t_begin + t + 1, sg0_next, sg1_next);
       }
       if (use_cpar) named_bar_sync(1, EPI_THREADS);
 
       const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && warp == 2 && lane == 0;
       if (tr) p.trace[t * 8 + 3] = clock64();
-      mbar_wait(&bars->s_full[b], (t / NSB) & 1);
-      if (tr) p.trace[t * 8 + 4] = clock64();
-      tc_fence_after();
 
-#pragma unroll 1
-      for (int cc = 0; cc < CPT; ++cc) {
-        const int ch = CPT * part + cc;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + static_cast<uint32_t>(b * BN + ch * 32), v);
-        tmem_ld_wait();
-        const uint32_t mwc = cc == 0 ? mw0 : mw1;
-
-        if (MODE == MODE_FWD) {
-          const float4 qp = make_float4(rp_reg[0], rp_reg[1], rp_reg[2], rp_reg[3]);
-          const float2* colp = reinterpret_cast<const float2*>(cpar_s) + ch * 32;
-          if (__any_sync(0xffffffffu, mwc != 0u)) fwd_chunk<LM, LOGQ, true>(v, mwc, qp, colp, st);
-          else fwd_chunk<LM, LOGQ, false>(v, mwc, qp, colp, st);
-        } else if (MODE == MODE_GRAD) {
-          uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
+      for (int k = 0; k < UPT; ++k) {
+        const int ucol = part * PW + k * UW;          // first tile column of this unit
+        // ---- the unit's scores arrive in registers
+        tmem_ld_wait_unit<UW>(v);
+        if (tr && k == 0) p.trace[t * 8 + 4] = clock64();
+        uint32_t s[UW];
+#pragma unroll
+        for (int c = 0; c < UW; ++c) s[c] = v[c];
+        // ---- start the next unit's load (next tile: hand the buffer back first, and only if its scores are ready)
+        bool pending = false;                          // next tile's first load still to be issued after the math
+        if (k + 1 < UPT) {
+          tmem_ld_unit<UW>(buf_addr + static_cast<uint32_t>((k + 1) * UW), v);
+        } else {
+          if (!HAS_G) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->s_empty[b]);
+          }
+          if (t + 1 < T) {
+            const int nb = (t + 1) % NSB;
+            const bool ready = __all_sync(0xffffffffu, mbar_try_wait(&bars->s_full[nb], ((t + 1) / NSB) & 1));
+            if (ready) {
+              tc_fence_after();
+              tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, v);
+            } else {
+              pending = true;
+            }
+          }
+        }
+        // ---- the unit's math
+        const uint32_t mwu = (k * UW < 32) ? mw0 : mw1;
+        const uint32_t mu = (UW == 32) ? mwu : ((mwu >> ((k * UW) & 31)) & 0xffffu);
+
+        if constexpr (MODE == MODE_FWD) {
+          const float4 qp = make_float4(rp_reg[0], rp_reg[1], rp_reg[2], rp_reg[3]);
+          const float2* colp = reinterpret_cast<const float2*>(cpar_s) + ucol;
+          if (__any_sync(0xffffffffu, mu != 0u)) fwd_unit<LM, LOGQ, true>(s, mu, qp, colp, st);
+          else fwd_unit<LM, LOGQ, false>(s, mu, qp, colp, st);
+        } else if constexpr (MODE == MODE_GRAD && EXPFAST) {
+          uint32_t pk[8];
+          const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
+          float2 us = make_float2(0.f, 0.f);
+          if (__any_sync(0xffffffffu, mu != 0u)) grad_fast_unit<QROW && LOGQ, true>(s, mu, xa, xo, lqp, us, pk);
+          else grad_fast_unit<QROW && LOGQ, false>(s, mu, xa, xo, lqp, us, pk);
+          rs2 = fadd2(rs2, us);
+          if (FOLDED) {
+            // row sums need the column signs; a unit with negative-sign columns (signed targets) re-adds those
+            const uint32_t sgw = (k * UW < 32) ? sg0 : sg1;
+            const uint32_t su = (sgw >> ((k * UW) & 31)) & 0xffffu;
+            if (su != 0u) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const uint32_t h = (c & 1) ? (pk[c >> 1] & 0xffff0000u) : (pk[c >> 1] << 16);
+                if ((su >> c) & 1u) rneg += __uint_as_float(h);
+              }
+            }
+          }
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
+        } else if constexpr (MODE == MODE_GRAD) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
             float g[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const int col = ch * 32 + c + u;
-              const float S = __uint_as_float(v[c + u]);
+              const int col = ucol + c + u;
+              const float S = __uint_as_float(s[c + u]);
               float gv, hv;
               if (QROW) {
                 float lq2 = 0.f;
@@ -731,7 +842,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 }
                 grad_elem<LM, LOGQ>(S, rp_reg[1], qp, gv, hv);
               }
-              const bool masked = (mwc >> (c + u)) & 1u;
+              const bool masked = (mu >> (c + u)) & 1u;
               hv = masked ? 0.f : hv;
               gv = masked ? 0.f : gv + hv;
               rgh += hv;
@@ -740,56 +851,54 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             rg += g[0] + g[1];
             pk[c >> 1] = pack_bf16x2(g[0], g[1]);
           }
-          // the G buffer must have been consumed by its previous second MMA before it is overwritten
-          if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
-          tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
-        } else if (MODE == MODE_DEBUG) {
-          uint32_t pk[16];
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
+        } else if constexpr (MODE == MODE_DEBUG) {
+          uint32_t pk[8];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float a = __uint_as_float(v[c]), bb = __uint_as_float(v[c + 1]);
+          for (int c = 0; c < 16; c += 2) {
+            float a = __uint_as_float(s[c]), bb = __uint_as_float(s[c + 1]);
             if (p.dbg_s != nullptr) {
-              float* d = p.dbg_s + static_cast<size_t>(row) * (static_cast<size_t>(p.n_ctiles) * BN) + j0 + ch * 32 + c;
+              float* d = p.dbg_s + static_cast<size_t>(row) * (static_cast<size_t>(p.n_ctiles) * BN) + j0 + ucol + c;
               d[0] = a;
               d[1] = bb;
             }
-            a = ((mwc >> c) & 1u) ? 0.f : a;
-            bb = ((mwc >> (c + 1)) & 1u) ? 0.f : bb;
+            a = ((mu >> c) & 1u) ? 0.f : a;
+            bb = ((mu >> (c + 1)) & 1u) ? 0.f : bb;
             rg += a + bb;
             pk[c >> 1] = pack_bf16x2(a, bb);
           }
-          if (cc == 0) mbar_wait(&bars->g_empty[gb], ((t / g_bufs) & 1) ^ 1);
-          tmem_st16(tmem_base + lane_off + g_col0 + static_cast<uint32_t>(gb * 64 + ch * 16), pk);
-        } else if (MODE == MODE_TOPK) {
-          // Streaming selection.  Fast path: one fmax per element against the row's threshold.  A chunk in which
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
+        } else if constexpr (MODE == MODE_TOPK) {
+          // Streaming selection.  Fast path: one fmax per element against the row's threshold.  A unit in which
           // some row can beat its current k-th best is staged in shared memory and each such row is then scanned by
           // all 32 lanes at once (ballot + popc-compacted, coalesced appends) - rows hit rarely, warps hit often.
+          const uint32_t mwc = mu;
           uint32_t w[32];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
           bool hit;
           if (!p.topk_mining) {
-            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+            float m0 = __uint_as_float(s[0]), m1 = __uint_as_float(s[1]), m2 = __uint_as_float(s[2]), m3 = __uint_as_float(s[3]);
 #pragma unroll
             for (int c = 4; c < 32; c += 4) {
-              m0 = fmaxf(m0, __uint_as_float(v[c]));
-              m1 = fmaxf(m1, __uint_as_float(v[c + 1]));
-              m2 = fmaxf(m2, __uint_as_float(v[c + 2]));
-              m3 = fmaxf(m3, __uint_as_float(v[c + 3]));
+              m0 = fmaxf(m0, __uint_as_float(s[c]));
+              m1 = fmaxf(m1, __uint_as_float(s[c + 1]));
+              m2 = fmaxf(m2, __uint_as_float(s[c + 2]));
+              m3 = fmaxf(m3, __uint_as_float(s[c + 3]));
             }
             hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) w[c] = v[c];
+            for (int c = 0; c < 32; ++c) w[c] = s[c];
           } else {
             // mining: key = bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by R asc);
             // mode 2 mirrors the order (see mined_forward_kernel)
             uint32_t kmax = 0;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const float S = __uint_as_float(v[c]);
+              const float S = __uint_as_float(s[c]);
               // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
               //  per-tile barrier, so a compacting warp never stalls the others)
               float l2 = rp_reg[0] * S;                         // norms ride in the contraction
               if (LOGQ) {
-                const int jc = min(j0 + ch * 32 + c, p.nC - 1);
+                const int jc = min(j0 + ucol + c, p.nC - 1);
                 l2 -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
               }
               float r = l2 + rp_reg[2];                        // rp_reg[2] = -L2_ii: R = L_ij - L_ii
@@ -798,26 +907,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               } else {
                 r += 0.0f;                                     // -0 -> +0 (losses.py:149 tests `< 0`)
               }
-              uint32_t k = __float_as_uint(r) ^ 0x7fffffffu;
-              k = (r != r) ? 1u : max(k, 1u);
-              w[c] = k;
-              kmax = max(kmax, k);
+              uint32_t kk = __float_as_uint(r) ^ 0x7fffffffu;
+              kk = (r != r) ? 1u : max(kk, 1u);
+              w[c] = kk;
+              kmax = max(kmax, kk);
             }
             hit = kmax > thr;
           }
           uint32_t hm = __ballot_sync(0xffffffffu, hit);
           if (hm) {
-            uint32_t* st = sStage + ((warp - 2) * 32) * TOPK_STAGE_STRIDE;
+            uint32_t* stg = sStage + ((warp - 2) * 32) * TOPK_STAGE_STRIDE;
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4)
-              *reinterpret_cast<uint4*>(st + lane * TOPK_STAGE_STRIDE + q4 * 4) =
+              *reinterpret_cast<uint4*>(stg + lane * TOPK_STAGE_STRIDE + q4 * 4) =
                   make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
             __syncwarp();
-            const uint32_t col = static_cast<uint32_t>(j0 + ch * 32 + lane);
+            const uint32_t col = static_cast<uint32_t>(j0 + ucol + lane);
             while (hm) {
               const int src = __ffs(hm) - 1;
               hm &= hm - 1;
-              const uint32_t x = st[src * TOPK_STAGE_STRIDE + lane];
+              const uint32_t x = stg[src * TOPK_STAGE_STRIDE + lane];
               const uint32_t m_src = __shfl_sync(0xffffffffu, mwc, src);
               const int cnt_src = __shfl_sync(0xffffffffu, cnt, src);
               bool pass;
@@ -862,15 +971,21 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             }
           }
         }
+        // ---- the next tile's scores were not ready before the math: wait for them now
+        if (pending) {
+          const int nb = (t + 1) % NSB;
+          mbar_wait(&bars->s_full[nb], ((t + 1) / NSB) & 1);
+          tc_fence_after();
+          tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, v);
+        }
       }
-      // accumulator buffer b fully read -> hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(&bars->s_empty[b]);
       if (tr) p.trace[t * 8 + 5] = clock64();
       if (HAS_G) {
+        // G tile of this warp is in TMEM -> the MMA warp may issue the second MMA of the tile
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars->g_full[gb]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->g_full[b]);
       }
     }
 
@@ -885,12 +1000,20 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       tc_fence_after();
       float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
       for (int cc = part; cc < p.kp / 32; cc += EP) {   // accumulator chunks are dealt round-robin to the parts
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + acc_col + static_cast<uint32_t>(cc * 32), v);
-        tmem_ld_wait();
+        uint32_t a[32];
+        tmem_ld32(tmem_base + lane_off + acc_col + static_cast<uint32_t>(cc * 32), a);
+        tmem_ld_wait32(a);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<uint4*>(o + cc * 32 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 32; c += 4) {
+          float4 x = make_float4(__uint_as_float(a[c]), __uint_as_float(a[c + 1]), __uint_as_float(a[c + 2]),
+                                 __uint_as_float(a[c + 3]));
+          if (EXPFAST) { x.x *= oscale; x.y *= oscale; x.z *= oscale; x.w *= oscale; }
+          *reinterpret_cast<float4*>(o + cc * 32 + c) = x;
+        }
+      }
+      if (EXPFAST) {
+        rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
+        rgh = 0.f;
       }
       *reinterpret_cast<float2*>(p.out_stats + out_row * 2) = make_float2(rg, rgh);
     }
