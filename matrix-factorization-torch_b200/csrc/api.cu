@@ -158,6 +158,7 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
   for (int ns = MAX_STAGES; ns >= (has_g ? 2 : 1); --ns) {
     const SweepSmemLayout lay = sweep_smem_layout(kp, parts, ns, aug, cpar_floats, topk_warps);
     if (lay.total <= SMEM_BUDGET) {
+      if (!has_g && ns == 3) continue;   // the two score issuers of the forward / top-k sweeps need an even ring
       pl.nstages = ns;
       pl.smem = lay.total;
       pl.ok = true;

@@ -17,7 +17,8 @@
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then 4*EP epilogue warps:
+// Warp roles: 4*EP epilogue warps, then the TMA producer warp, then the TMEM allocator + MMA issuer warp (the highest
+// warp id has issue priority on its scheduler: the thread that feeds the tensor core must never queue behind math):
 // thread <-> (TMEM lane = tile row, column part).  EP = 4 (16 epilogue warps) for the single-loss forward / gradient
 // variants, EP = 2 where register pressure is high (all-losses variants, top-k).
 //
@@ -47,6 +48,12 @@ constexpr uint32_t TMEM_COLS = 512;
 // offset), so a buffer is S, then G, then free again once its second MMA has been issued.
 __host__ __device__ constexpr int grad_bufs(int kp) { return (512 - kp) / 128 >= 3 ? 3 : 2; }
 constexpr int MAX_STAGES = 4;
+// per-tile clock stamps of CTA (0,0) (xb_debug_set_trace): compiled in only with -DXB_TRACE, the stamps cost issue slots
+#ifdef XB_TRACE
+constexpr bool XB_TRACE_ON = true;
+#else
+constexpr bool XB_TRACE_ON = false;
+#endif
 
 enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3 };
 
@@ -58,6 +65,8 @@ __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) ==
 __host__ __device__ constexpr int epi_parts(int mode, int lm, bool /*qrow*/) {
   return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
 }
+// threads per CTA: epilogue warps + TMA producer warp + two MMA issuer warps
+__host__ __device__ constexpr int sweep_threads(int mode, int lm, bool qrow) { return 96 + 128 * epi_parts(mode, lm, qrow); }
 // single-loss gradient kernels of the exponential losses take the lean path: |G| = 2^x, signs and per-row /
 // per-column factors folded into offsets, operands and the final write-out
 __host__ __device__ constexpr bool grad_expfast(int lm) { return lm_single(lm) && (lm & (2 | 4)) != 0; }
@@ -239,7 +248,6 @@ __device__ __forceinline__ void fwd_unit(const uint32_t (&s)[16], uint32_t m16, 
       st.lsum += g0 + g1;
     }
   }
-  st.cnt += static_cast<float>(16 - __popc(m16));
 }
 
 // Lean gradient unit of the exponential losses: |G| = 2^(xa * S + xo [- lq2_col]), masked columns -> 0, row sum in
@@ -428,6 +436,18 @@ __device__ __forceinline__ float order_key_inv(uint32_t k) {
 }
 
 // =================================================================================================
+// position in a ring of n buffers + phase parity of the current lap (no integer division in the hot loops)
+struct Ring {
+  int i = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++i == n) {
+      i = 0;
+      ph ^= 1u;
+    }
+  }
+};
+
 template <int UW>
 __device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&v)[UW]) {
   if constexpr (UW == 16) tmem_ld16(taddr, v);
@@ -440,7 +460,7 @@ __device__ __forceinline__ void tmem_ld_wait_unit(uint32_t (&v)[UW]) {
 }
 
 template <int MODE, int LM, bool QROW, bool LOGQ>
-__global__ void __launch_bounds__(64 + 128 * epi_parts(MODE, LM, QROW), 1)
+__global__ void __launch_bounds__(sweep_threads(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
              const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmCa, const SweepParams p) {
   constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
@@ -493,7 +513,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(&bars->s_full[b], 1);
-      mbar_init(&bars->s_empty[b], EPI_WARPS);
+      mbar_init(&bars->s_empty[b], HAS_G ? 1 : EPI_WARPS);   // GRAD: released by the commit of the tile's second MMA
       mbar_init(&bars->g_full[b], EPI_WARPS);
     }
     mbar_init(&bars->acc_full, 1);
@@ -505,13 +525,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       tma_prefetch_desc(&tmCa);
     }
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, MMA_WARP2 = EPI_WARPS + 2;
+  if (warp == MMA_WARP) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ======================================================================== TMA producer
     if (lane == 0 && T > 0) {
       const uint32_t aug_bytes = aug ? AUG_BYTES : 0u;
@@ -520,11 +541,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         for (int kb = 0; kb < kb_n; ++kb)
           tma_load_2d(sR + (pt * kb_n + kb) * BLOCK_BYTES, &tmR, &bars->r_full, pt * p.kp + kb * KBLK, rb * BM);
       if (aug) tma_load_2d(sRa, &tmRa, &bars->r_full, 0, rb * BM);              // row-role columns [0,16)
-      for (int t = 0; t < T; ++t) {
-        const int s = t % NS;
-        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles;
+      Ring st;
+      for (int t = 0; t < T; ++t, st.advance(NS)) {
+        const int s = st.i;
+        const bool tr = XB_TRACE_ON && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles;
         if (tr) p.trace[t * 8 + 6] = clock64();
-        mbar_wait(&bars->c_empty[s], ((t / NS) & 1) ^ 1);
+        mbar_wait(&bars->c_empty[s], st.ph ^ 1u);
         if (tr) p.trace[t * 8 + 7] = clock64();
         mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes + aug_bytes);
         uint8_t* dst = sC + static_cast<size_t>(s) * tile_bytes;
@@ -535,11 +557,17 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         if (aug) tma_load_2d(sCa + s * AUG_BYTES, &tmCa, &bars->c_full[s], 16, (t_begin + t) * BN);   // column role
       }
     }
-  } else if (warp == 1) {
-    // ======================================================================== MMA issuer
-    // The whole warp runs this loop in lock-step (uniform control flow, every lane polls the barriers); one
-    // elected lane issues the tcgen05 instructions.  One thread feeds the tensor core for the whole CTA, so the
-    // per-MMA issue cost is kept to a couple of 32-bit adds.
+  } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+    // ======================================================================== MMA issuers
+    // tcgen05.mma issue is (nearly) synchronous: the issuing thread stalls until the tensor pipe accepts the
+    // instruction, i.e. for about as long as the MMAs take to execute.  With one issuer the barrier round trips of the
+    // next tile could only start once the pipe had drained; so there are TWO issuer warps whose waits hide behind
+    // each other's MMAs:  FWD / TOPK: warp A takes the even score tiles, warp B the odd ones;
+    //                     GRAD:       warp A issues every score tile, warp B every second MMA (acc += G . C).
+    // Each warp runs its loop in lock-step (uniform control flow, every lane polls the barriers); one elected lane
+    // issues.  Buffer hand-back: s_empty[b] is armed by the epilogue (FWD / TOPK) or by the commit that follows the
+    // tile's second MMA (GRAD: the G tile lives in the score buffer).
+    const bool second = warp == MMA_WARP2;
     if (T > 0) {
       const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
       const uint32_t idesc_g = umma_idesc_bf16(BM, static_cast<uint32_t>(p.kp), 0, 1);
@@ -553,15 +581,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const uint32_t part_lo = static_cast<uint32_t>(kb_n) * blk_lo;
       const uint32_t acc_tmem = tmem_base + acc_col;
 
+      Ring sb, ss;   // TMEM buffer ring, stage ring (position of the tile being issued)
       auto issue_scores = [&](int t) {
-        const int b = t % NSB, s = t % NS;
-        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && lane == 0;
+        const int b = sb.i, s = ss.i;
+        const bool tr = XB_TRACE_ON && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && lane == 0;
         if (tr) p.trace[t * 8 + 0] = clock64();
-        // FWD / TOPK: the epilogue hands the buffer back.  GRAD: buffer b last held tile t - NSB, whose second MMA
-        // this thread has already issued - tcgen05.mma of one thread execute in issue order, so no barrier is needed.
-        if (!HAS_G) mbar_wait(&bars->s_empty[b], ((t / NSB) & 1) ^ 1);
+        mbar_wait(&bars->s_empty[b], sb.ph ^ 1u);
         if (tr) p.trace[t * 8 + 1] = clock64();
-        mbar_wait(&bars->c_full[s], (t / NS) & 1);
+        mbar_wait(&bars->c_full[s], ss.ph);
         if (tr) p.trace[t * 8 + 2] = clock64();
         tc_fence_after();
         if (elect_one()) {
@@ -599,20 +626,42 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         __syncwarp();
       };
 
-      mbar_wait(&bars->r_full, 0);
-      if (!HAS_G) {
-        for (int t = 0; t < T; ++t) issue_scores(t);
-      } else {
-        // score tiles run AHEAD tiles in front of the second MMA: G(t) is being computed by the epilogue while the
-        // tensor core already holds S(t+1) .. S(t+AHEAD), so neither side waits for the other in steady state
-        int ahead = NSB - 1;
-        if (ahead > NS - 1) ahead = NS - 1;
-        for (int t = 0; t < ahead && t < T; ++t) issue_scores(t);
+      if (!HAS_G && (NS & 1) == 0) {
+        // (an even ring depth keeps every stage with one issuer, so a parity wait can never be a lap behind)
+        mbar_wait(&bars->r_full, 0);
+        if (second) {
+          sb.advance(NSB);
+          ss.advance(NS);
+        }
+        for (int t = second ? 1 : 0; t < T; t += 2) {
+          issue_scores(t);
+          sb.advance(NSB);
+          sb.advance(NSB);
+          ss.advance(NS);
+          ss.advance(NS);
+        }
+      } else if (!HAS_G) {
+        // odd ring depth (shared memory only fits one or three stages): a single issuer
+        if (!second) {
+          mbar_wait(&bars->r_full, 0);
+          for (int t = 0; t < T; ++t) {
+            issue_scores(t);
+            sb.advance(NSB);
+            ss.advance(NS);
+          }
+        }
+      } else if (!second) {
+        mbar_wait(&bars->r_full, 0);
         for (int t = 0; t < T; ++t) {
-          if (t + ahead < T) issue_scores(t + ahead);
-          const int s = t % NS;
-          const int b = t % NSB;
-          mbar_wait(&bars->g_full[b], (t / NSB) & 1);
+          issue_scores(t);
+          sb.advance(NSB);
+          ss.advance(NS);
+        }
+      } else {
+        for (int t = 0; t < T; ++t, sb.advance(NSB), ss.advance(NS)) {
+          const int s = ss.i;
+          const int b = sb.i;
+          mbar_wait(&bars->g_full[b], sb.ph);
           tc_fence_after();
           if (elect_one()) {
             // acc[128 x kp] += G[128 x 128] . C_tile[128 x kp]: A = G from TMEM (K-step kk = 8 packed columns at
@@ -628,7 +677,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 acc = 1;
               }
             }
-            umma_commit(&bars->c_empty[s]);
+            umma_commit(&bars->c_empty[s]);   // stage and score/G buffer are free again
+            umma_commit(&bars->s_empty[b]);
           }
           __syncwarp();
         }
@@ -639,9 +689,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   } else if (T > 0) {
     // ======================================================================== epilogue warps
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int part = (warp - 2) >> 2;               // column part of the tile this warp reduces
+    const int part = warp >> 2;                     // column part of the tile this warp reduces
     const int row_l = quad * 32 + lane;             // tile row == TMEM lane
-    const int e_tid = threadIdx.x - 64;             // 0..EPI_THREADS-1, used for cooperative parameter loads
+    const int e_tid = threadIdx.x;                  // 0..EPI_THREADS-1, used for cooperative parameter loads
     const int row = rb * BM + row_l;
     const bool row_ok = row < p.nR;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -672,6 +722,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     const uint32_t* mrow = (p.mask != nullptr) ? p.mask + static_cast<size_t>(row) * p.mask_words : nullptr;
 
     FwdState<LM> st;
+    int ucnt = 0;
     float2 rs2 = make_float2(0.f, 0.f);             // GRAD lean path: packed row sum of |G|
     float rneg = 0.f;                               //   ... part of it that belongs to negative-sign columns
     float rg = 0.f, rgh = 0.f;                      // GRAD generic path: row sums of G (all / hinge+logistic part)
@@ -728,14 +779,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     fetch_cpar(t_begin, cpar_next);
     fetch_sign(t_begin, sg0_next, sg1_next);
 
-    // first unit of the first tile
-    uint32_t v[UW];
+    // first unit of the first tile.  Units alternate between two register sets (va: even units, vb: odd units), so the
+    // load of the next unit lands while the current one is being reduced and nothing is ever copied.
+    uint32_t va[UW], vb[UW];
     mbar_wait(&bars->s_full[0], 0);
     tc_fence_after();
-    tmem_ld_unit<UW>(tmem_base + lane_off + part_col, v);
+    tmem_ld_unit<UW>(tmem_base + lane_off + part_col, va);
 
-    for (int t = 0; t < T; ++t) {
-      const int b = t % NSB;
+    Ring eb;   // TMEM buffer ring of the epilogue
+    for (int t = 0; t < T; ++t, eb.advance(NSB)) {
+      const int b = eb.i;
+      const int nb = (b + 1 == NSB) ? 0 : b + 1;                  // next tile's buffer and phase parity
+      const uint32_t nph = (b + 1 == NSB) ? (eb.ph ^ 1u) : eb.ph;
       const int j0 = (t_begin + t) * BN;
       const uint32_t buf_addr = tmem_base + lane_off + static_cast<uint32_t>(b * BN) + part_col;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
@@ -749,6 +804,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
       }
       const uint32_t mw0 = mw0_next, mw1 = mw1_next, sg0 = sg0_next, sg1 = sg1_next;
+      if (MODE == MODE_FWD) ucnt += PW - __popc(mw0) - (PW == 64 ? __popc(mw1) : 0);   // unmasked columns of this row
       if (t + 1 < T) {
         fetch_mask(t_begin + t + 1, mw0_next, mw1_next);
         fetch_cpar(t_begin + t + 1, cpar_next);
@@ -756,22 +812,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       }
       if (use_cpar) named_bar_sync(1, EPI_THREADS);
 
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && warp == 2 && lane == 0;
+      const bool tr = XB_TRACE_ON && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles && warp == 0 && lane == 0;
       if (tr) p.trace[t * 8 + 3] = clock64();
 
-#pragma unroll
-      for (int k = 0; k < UPT; ++k) {
+      auto do_unit = [&](uint32_t (&cur)[UW], uint32_t (&nxt)[UW], const int k) __attribute__((always_inline)) {
         const int ucol = part * PW + k * UW;          // first tile column of this unit
+        // (probe the next tile's score barrier early: the answer is needed only after this unit's load has landed)
+        bool probe = false;
+        if (k + 1 == UPT && t + 1 < T) probe = mbar_try_wait(&bars->s_full[nb], nph);
         // ---- the unit's scores arrive in registers
-        tmem_ld_wait_unit<UW>(v);
+        tmem_ld_wait_unit<UW>(cur);
         if (tr && k == 0) p.trace[t * 8 + 4] = clock64();
-        uint32_t s[UW];
-#pragma unroll
-        for (int c = 0; c < UW; ++c) s[c] = v[c];
+        const uint32_t (&s)[UW] = cur;
         // ---- start the next unit's load (next tile: hand the buffer back first, and only if its scores are ready)
         bool pending = false;                          // next tile's first load still to be issued after the math
         if (k + 1 < UPT) {
-          tmem_ld_unit<UW>(buf_addr + static_cast<uint32_t>((k + 1) * UW), v);
+          tmem_ld_unit<UW>(buf_addr + static_cast<uint32_t>((k + 1) * UW), nxt);
         } else {
           if (!HAS_G) {
             tc_fence_before();
@@ -779,11 +835,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             if (lane == 0) mbar_arrive(&bars->s_empty[b]);
           }
           if (t + 1 < T) {
-            const int nb = (t + 1) % NSB;
-            const bool ready = __all_sync(0xffffffffu, mbar_try_wait(&bars->s_full[nb], ((t + 1) / NSB) & 1));
+            const bool ready = __all_sync(0xffffffffu, probe);
             if (ready) {
               tc_fence_after();
-              tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, v);
+              tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
             } else {
               pending = true;
             }
@@ -916,7 +971,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
           uint32_t hm = __ballot_sync(0xffffffffu, hit);
           if (hm) {
-            uint32_t* stg = sStage + ((warp - 2) * 32) * TOPK_STAGE_STRIDE;
+            uint32_t* stg = sStage + (warp * 32) * TOPK_STAGE_STRIDE;
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4)
               *reinterpret_cast<uint4*>(stg + lane * TOPK_STAGE_STRIDE + q4 * 4) =
@@ -973,11 +1028,16 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
         // ---- the next tile's scores were not ready before the math: wait for them now
         if (pending) {
-          const int nb = (t + 1) % NSB;
-          mbar_wait(&bars->s_full[nb], ((t + 1) / NSB) & 1);
+          mbar_wait(&bars->s_full[nb], nph);
           tc_fence_after();
-          tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, v);
+          tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
         }
+      };
+      static_assert((UPT & 1) == 0, "units per tile must be even (register ping-pong)");
+#pragma unroll
+      for (int k = 0; k < UPT; k += 2) {
+        do_unit(va, vb, k);
+        do_unit(vb, va, k + 1);
       }
       if (tr) p.trace[t * 8 + 5] = clock64();
       if (HAS_G) {
@@ -992,7 +1052,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // ----------------------------------------------------------------------- unit epilogue
     if (MODE == MODE_FWD) {
       float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
-      o[0] = make_float4(st.cnt, st.csum, st.hsum, st.lsum);
+      o[0] = make_float4(static_cast<float>(ucnt), st.csum, st.hsum, st.lsum);
       o[1] = make_float4(st.mx, st.se, 0.f, 0.f);
     }
     if (HAS_G) {
@@ -1025,7 +1085,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 }  // namespace xb

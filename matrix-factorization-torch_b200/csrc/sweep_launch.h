@@ -23,7 +23,7 @@ inline cudaError_t launch_sweep_impl(K kernel, int mode, int lm, bool qrow, cons
                                      const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kernel<<<grid, 64 + 128 * epi_parts(mode, lm, qrow), smem, st>>>(tmR, tmC, tmRa, tmCa, p);
+  kernel<<<grid, sweep_threads(mode, lm, qrow), smem, st>>>(tmR, tmC, tmRa, tmCa, p);
   return cudaGetLastError();
 }
 }  // namespace xb
