@@ -8,12 +8,14 @@ caller raises (see ``require_cuda``).
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 
 import torch
 
 _PKG_DIR = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libxfmr_b200.so"
+# XB_LIB selects a debug build of the same library (e.g. the -DXB_TRACE one used by tests/quick_probe.py)
+LIB_PATH = pathlib.Path(os.environ["XB_LIB"]) if os.environ.get("XB_LIB") else _PKG_DIR / "libxfmr_b200.so"
 
 XB_OK = 0
 XB_DTYPE_F32 = 0
