@@ -291,6 +291,23 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
   return d;
 }
+// 2^x for a pair of values WITHOUT the special-function unit (FlashAttention-4 style): round to the nearest integer n
+// with the 1.5 * 2^23 trick, a cubic in f = x - n (|f| <= 0.5, relative error 7.5e-5), and n added straight into the
+// exponent field.  x is clamped to [-125, 126].  Used for a fixed share of the exponentials so that the MUFU pipe
+// (16 results per clock and SM) and the FMA pipe finish a tile at about the same time.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -125.f), 126.f);
+  x.y = fminf(fmaxf(x.y, -125.f), 126.f);
+  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(f, make_float2(0.055171459913253784f, 0.055171459913253784f),
+                   make_float2(0.2426108568906784f, 0.2426108568906784f));
+  q = ffma2(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = ffma2(q, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
 // two fp32 -> packed bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;

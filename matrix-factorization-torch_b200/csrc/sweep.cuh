@@ -73,7 +73,15 @@ __host__ __device__ constexpr bool grad_expfast(int lm) { return lm_single(lm) &
 // floats of per-query gradient parameters: single loss {a2, off, k, 0}; all {a2, (off,k) x 5, 0}
 __host__ __device__ constexpr int grad_qpar_floats(int lm) { return lm_single(lm) ? 4 : 12; }
 
-constexpr float NEG_BIG = -1.0e30f;      // "no value yet" for running maxima (finite: avoids inf-inf)
+constexpr float NEG_BIG = -1.0e30f;
+// pairs (of the 8 in a unit of 16 columns) whose exponentials are evaluated on the FMA pipe instead of MUFU
+#ifndef XB_POLY_PAIRS
+#define XB_POLY_PAIRS 2
+#endif
+constexpr int POLY_PAIRS = XB_POLY_PAIRS;
+__device__ __forceinline__ float2 ex2_pair(float2 x, int pair) {
+  return pair < POLY_PAIRS ? ex2_poly2(x) : make_float2(ex2f(x.x), ex2f(x.y));
+}      // "no value yet" for running maxima (finite: avoids inf-inf)
 
 struct SweepParams {
   int nR, nC;           // valid rows of the row / column operand
@@ -113,7 +121,7 @@ struct SweepParams {
 struct SweepSmemLayout {
   uint32_t r_off, c_off, ra_off, ca_off, par_off, bar_off, stage_off, total;
 };
-constexpr int TOPK_STAGE_STRIDE = 36;   // words per staged row (16-byte aligned, conflict-free 128-bit stores)
+constexpr int TOPK_STAGE_STRIDE = 20;   // words per staged row of 16 (16-byte aligned, conflict-free 128-bit stores)
 
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, int nstages, bool aug,
                                                              int cpar_floats, int topk_warps = 0) {
@@ -190,8 +198,8 @@ __device__ __forceinline__ void fwd_unit(const uint32_t (&s)[16], uint32_t m16, 
     float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
-      a0 = fadd2(a0, make_float2(ex2f(L[c]), ex2f(L[c + 1])));
-      a1 = fadd2(a1, make_float2(ex2f(L[c + 2]), ex2f(L[c + 3])));
+      a0 = fadd2(a0, ex2_pair(make_float2(L[c], L[c + 1]), c >> 1));
+      a1 = fadd2(a1, ex2_pair(make_float2(L[c + 2], L[c + 3]), (c >> 1) + 1));
     }
     const float t = (a0.x + a0.y) + (a1.x + a1.y);
     if (!fresh && t <= 1.0e12f) {
@@ -264,7 +272,8 @@ __device__ __forceinline__ void grad_fast_unit(const uint32_t (&s)[16], uint32_t
       x.x -= cp.y;
       x.y -= cp.w;
     }
-    float e0 = ex2f(x.x), e1 = ex2f(x.y);
+    const float2 e = ex2_pair(x, c >> 1);
+    float e0 = e.x, e1 = e.y;
     if (MASKED) {
       e0 = ((m16 >> c) & 1u) ? 0.f : e0;
       e1 = ((m16 >> (c + 1)) & 1u) ? 0.f : e1;
@@ -466,7 +475,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
   constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
   constexpr int PW = BN / EP;                            // tile columns owned by one epilogue thread
-  constexpr int UW = (MODE == MODE_TOPK) ? 32 : 16;      // columns per unit
+  constexpr int UW = 16;                                 // columns per unit
   constexpr int UPT = PW / UW;                           // units per thread and tile
   constexpr int EPI_WARPS = 4 * EP;
   constexpr int EPI_THREADS = 128 * EP;
@@ -924,30 +933,28 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
           tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (MODE == MODE_TOPK) {
-          // Streaming selection.  Fast path: one fmax per element against the row's threshold.  A unit in which
-          // some row can beat its current k-th best is staged in shared memory and each such row is then scanned by
-          // all 32 lanes at once (ballot + popc-compacted, coalesced appends) - rows hit rarely, warps hit often.
-          const uint32_t mwc = mu;
-          uint32_t w[32];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
+          // Streaming selection.  Fast path: one 3-input max per two elements against the row's threshold.  A unit in
+          // which some row can beat its current k-th best is staged in shared memory and the hit rows are then scanned
+          // two at a time, one per half-warp (ballot + popc-compacted appends) - rows hit rarely, warps hit often.
+          constexpr bool MINING = LM != 0;
+          uint32_t w[16];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
           bool hit;
-          if (!p.topk_mining) {
-            float m0 = __uint_as_float(s[0]), m1 = __uint_as_float(s[1]), m2 = __uint_as_float(s[2]), m3 = __uint_as_float(s[3]);
-#pragma unroll
-            for (int c = 4; c < 32; c += 4) {
-              m0 = fmaxf(m0, __uint_as_float(s[c]));
-              m1 = fmaxf(m1, __uint_as_float(s[c + 1]));
-              m2 = fmaxf(m2, __uint_as_float(s[c + 2]));
-              m3 = fmaxf(m3, __uint_as_float(s[c + 3]));
-            }
+          if (!MINING) {
+            float m0 = fmaxf(__uint_as_float(s[0]), fmaxf(__uint_as_float(s[1]), __uint_as_float(s[2])));
+            float m1 = fmaxf(__uint_as_float(s[3]), fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5])));
+            float m2 = fmaxf(__uint_as_float(s[6]), fmaxf(__uint_as_float(s[7]), __uint_as_float(s[8])));
+            float m3 = fmaxf(__uint_as_float(s[9]), fmaxf(__uint_as_float(s[10]), __uint_as_float(s[11])));
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[12]), __uint_as_float(s[13])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[14]), __uint_as_float(s[15])));
             hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) w[c] = s[c];
+            for (int c = 0; c < 16; ++c) w[c] = s[c];
           } else {
             // mining: key = bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by R asc);
             // mode 2 mirrors the order (see mined_forward_kernel)
             uint32_t kmax = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+            for (int c = 0; c < 16; ++c) {
               const float S = __uint_as_float(s[c]);
               // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
               //  per-tile barrier, so a compacting warp never stalls the others)
@@ -973,20 +980,28 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           if (hm) {
             uint32_t* stg = sStage + (warp * 32) * TOPK_STAGE_STRIDE;
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4)
+            for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(stg + lane * TOPK_STAGE_STRIDE + q4 * 4) =
                   make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
             __syncwarp();
-            const uint32_t col = static_cast<uint32_t>(j0 + ucol + lane);
+            const int half = lane >> 4, hl = lane & 15;
+            const uint32_t col = static_cast<uint32_t>(j0 + ucol + hl);
             while (hm) {
-              const int src = __ffs(hm) - 1;
+              const int srcA = __ffs(hm) - 1;
               hm &= hm - 1;
-              const uint32_t x = stg[src * TOPK_STAGE_STRIDE + lane];
-              const uint32_t m_src = __shfl_sync(0xffffffffu, mwc, src);
+              int srcB = -1;
+              if (hm) {
+                srcB = __ffs(hm) - 1;
+                hm &= hm - 1;
+              }
+              const bool act = half == 0 || srcB >= 0;
+              const int src = (half != 0 && srcB >= 0) ? srcB : srcA;
+              const uint32_t x = stg[src * TOPK_STAGE_STRIDE + hl];
+              const uint32_t m_src = __shfl_sync(0xffffffffu, mu, src);
               const int cnt_src = __shfl_sync(0xffffffffu, cnt, src);
               bool pass;
               uint32_t key;
-              if (!p.topk_mining) {
+              if (!MINING) {
                 const float t_src = __shfl_sync(0xffffffffu, thr_f, src);
                 const float S = __uint_as_float(x);
                 pass = S >= t_src;
@@ -996,20 +1011,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 pass = x > t_src;
                 key = x;
               }
-              pass = pass && !((m_src >> lane) & 1u);
+              pass = pass && act && !((m_src >> hl) & 1u);
               const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+              const uint32_t pmh = half ? (pm >> 16) : (pm & 0xffffu);
               if (pass) {
                 unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
-                buf[cnt_src + __popc(pm & ((1u << lane) - 1u))] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~col);
+                buf[cnt_src + __popc(pmh & ((1u << hl) - 1u))] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~col);
               }
-              if (lane == src) cnt += __popc(pm);
+              if (lane == srcA) cnt += __popc(pm & 0xffffu);
+              if (lane == srcB) cnt += __popc(pm >> 16);
             }
             __syncwarp();
           }
-          // compaction: a row whose buffer cannot absorb another 32 candidates is reduced by its warp to the best
+          // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
           // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
           // column wins ties).
-          uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 32);
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
