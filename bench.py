@@ -52,6 +52,15 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic() -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum per sweep launch, from the committed `ncu --set full` capture of
+    this same command (profiles/ncu_traffic.json, written by profiles/ncu_summarize.py); None if it is absent."""
+    path = ROOT / "profiles" / "ncu_traffic.json"
+    if not path.exists():
+        return None
+    return float(json.loads(path.read_text())["sweep_dram_bytes_per_launch"])
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -245,7 +254,9 @@ def run_reference(args: argparse.Namespace) -> None:
 
 
 def bench_retrieval(device: torch.device, world: int, rank: int, num_items_total: int, num_queries: int, k: int) -> dict:
-    """Exact top-k over a row-sharded catalog (config 5 shape, catalog size reduced by default)."""
+    """Exact top-k over a row-sharded catalog (config 5: 65,536 queries x 10^8 items, d=128 bf16, k=100; strong
+    scaling - the catalog is split across the ranks, every rank scores all queries against its shard and the per-shard
+    top-k lists are all-gathered and merged)."""
     import torch.distributed as dist  # noqa: PLC0415
 
     import xfmr_b200  # noqa: PLC0415
@@ -282,7 +293,9 @@ def bench_retrieval(device: torch.device, world: int, rank: int, num_items_total
     del items
     return {"metric": "exact_top100_queries_per_s", "value": num_queries / (ms * 1e-3), "unit": "queries/s",
             "workload": f"{num_queries} queries x {num_items_total} items (sharded {world} ways), d=128 bf16, k={k}",
-            "ms": ms, "tensor_frac_of_burst_peak": flops / (ms * 1e-3) / (pk["bf16_tflops"] * 1e12)}
+            "ms": ms, "scaling": "strong", "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+            "tensor_frac_of_sustained_peak": flops / (ms * 1e-3) / (pk["bf16_tflops_sustained"] * 1e12),
+            "tensor_frac_of_burst_peak": flops / (ms * 1e-3) / (pk["bf16_tflops"] * 1e12)}
 
 
 def bench_gather(device: torch.device) -> dict:
@@ -309,7 +322,8 @@ def main() -> None:  # noqa: PLR0915
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (skip per-loss / retrieval / gather / cpu baseline)")
-    ap.add_argument("--retrieval-items", type=int, default=8_000_000, help="catalog rows of the retrieval extra (config 5 is 100,000,000)")
+    ap.add_argument("--retrieval-items", type=int, default=100_000_000,
+                    help="catalog rows of the retrieval extra, summed over all ranks (config 5: 100,000,000 = 25.6 GB bf16)")
     ap.add_argument("--retrieval-queries", type=int, default=65_536)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -427,7 +441,7 @@ def main() -> None:  # noqa: PLR0915
         "eager_ms_per_step": eager_ms,
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": ncu_traffic(),
             "kernel": "xb::sweep_kernel (3 launches per step: loss statistics, dQ, dI)",
             "algorithmic_flops_per_step": algo_flops, "sweep_ms_per_step": sweep_ms_per_step,
             "sweep_launches_per_step": sweep_count / args.steps, "peak_source": pk["source"] + " sustained bf16",

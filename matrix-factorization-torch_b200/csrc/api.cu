@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -170,6 +171,16 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
 
 static inline int mask_words_for(int ncols) { return 4 * cdiv(ncols, BN); }
 
+// Single-loss calls of the exponential losses run the forward statistics and the query-side gradient in ONE sweep
+// (MODE_FWDQ); the two separate sweeps stay behind as a device-side fallback.  XB_MERGE_FWDQ=0 turns the merge off.
+static bool merged_fwdq(int lm, bool mining) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("XB_MERGE_FWDQ");
+    return e == nullptr || e[0] != '0';
+  }();
+  return enabled && !mining && grad_expfast(lm);
+}
+
 static inline int sweep_lm_from_mask(uint32_t loss_mask) {
   int lm = 0;
   if (loss_mask & ((1u << XB_LOSS_CONTRASTIVE) | (1u << XB_LOSS_ALIGNMENT_CONTRASTIVE))) lm |= LM_CONTR;
@@ -242,9 +253,9 @@ constexpr int MINE_OVERFETCH = 16;  // extra candidates per side re-scored exact
 struct LossWs {
   int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
   bool mining;
-  SweepPlan fwd, gq, gi;   // forward / mining sweep, dQ sweep, dI sweep
+  SweepPlan fwd, fq, gq, gi;   // forward / mining sweep, merged forward + dQ sweep, dQ sweep, dI sweep
   size_t qprep, iprep, qaug, iaug, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
-      ueff, qg, qs, qaugb, csign, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
+      ueff, flag, qg, qs, qaugb, csign, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
 
 static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
@@ -262,6 +273,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
   w->fwd = plan_sweep(B, N, w->kp, w->parts, false, true, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 0, true) : 0);
   w->gq = plan_sweep(B, N, w->kp, w->parts, true, true, 2);
+  w->fq = plan_sweep(B, N, w->kp, w->parts, true, true, 6);
   w->gi = plan_sweep(N, B, w->kp, w->parts, true, true, gq_floats);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -288,6 +300,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->rowstat = take(sizeof(float4) * B);
   w->rowloss = take(sizeof(float) * 7 * B);
   w->ueff = take(sizeof(float) * 8);
+  w->flag = take(sizeof(int) * 4);
   w->redpart = take(sizeof(double) * XB_NUM_LOSSES * cdiv(B, LOSS_RED_ROWS));
   w->qg = take(sizeof(float) * 12 * B);
   // operands of the item-major sweep with the per-query factors folded in (grad_fold_kernel)
@@ -310,7 +323,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
     w->cand = w->cand_cnt = w->sel = w->selcol = w->selL2 = off;
   }
   w->total = off;
-  return w->fwd.ok && w->gq.ok && w->gi.ok;
+  return w->fwd.ok && w->fq.ok && w->gq.ok && w->gi.ok;
 }
 
 static int check_loss_desc(const xb_loss_desc* d) {
@@ -397,9 +410,19 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;
     if ((rc = make_aug_map(&tmQa, ws + w.qaug, B))) return rc;
     if ((rc = make_aug_map(&tmIa, ws + w.iaug, N))) return rc;
-    {  // dQ sweep: rows = queries, columns = items
+    const bool merged = merged_fwdq(lm, w.mining);
+    int* flag = reinterpret_cast<int*>(ws + w.flag);
+    if (merged) {
+      // the forward pass left acc = sum_j 2^(x_ij - m_i) v_j per column chunk: scale it to the gradient
+      grad_merge_q_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+          B, w.B_pad, w.fq.nchunks, epi_parts(MODE_FWDQ, lm, true), w.kp, reinterpret_cast<const float*>(ws + w.part), qg,
+          accq, rsq, flag);
+      XB_LAUNCHED();
+    }
+    {  // dQ sweep: rows = queries, columns = items (with the merged forward: only as its fallback)
       SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
       p.use_aug = 1;
+      p.cond = merged ? flag : nullptr;
       p.rpar = qg;
       p.cpar = reinterpret_cast<float*>(ws + w.ipar);
       p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
@@ -594,10 +617,33 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
     if (!w.mining) {
       p.rpar = reinterpret_cast<float*>(ws + w.qfwd);
       p.out_stats = reinterpret_cast<float*>(ws + w.part);
+      int* flag = reinterpret_cast<int*>(ws + w.flag);
+      const bool merged = merged_fwdq(lm, w.mining);
+      if (merged) {
+        // forward statistics + unnormalised dQ accumulators in one sweep; rows whose sums leave the fp32 range raise
+        // `flag`, which switches on the plain forward sweep below (and the dQ sweep of the backward pass)
+        XB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, st));
+        SweepParams pq = base_params(B, N, w.kp, w.parts, w.fq);
+        pq.use_aug = 1;
+        pq.rpar = p.rpar;
+        pq.cpar = p.cpar;
+        pq.mask = p.mask;
+        pq.mask_words = p.mask_words;
+        pq.out_stats = p.out_stats;
+        pq.out_acc = reinterpret_cast<float*>(ws + w.accq);
+        XB_SWEEP(launch_sweep_fwdq(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, pq, dim3(w.fq.nchunks, w.fq.n_rblocks),
+                                   w.fq.smem, st));
+        loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fq.nchunks * epi_parts(MODE_FWDQ, lm, true), p.out_stats, desc->sigma,
+                                                       reinterpret_cast<float4*>(ws + w.rowinfo),
+                                                       reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, flag, nullptr);
+        XB_LAUNCHED();
+        p.cond = flag;
+      }
       XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
       loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
-                                                     reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
+                                                     reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr,
+                                                     merged ? flag : nullptr);
       XB_LAUNCHED();
     } else {
       // semi-hard mining (losses.py:134-162): streaming selection of the K best columns per row, then
@@ -631,7 +677,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
     // AlignmentLoss only: diagonal terms, no sweep.  An empty partial set gives cnt = 0.
     loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, w.B_pad, 0, nullptr, desc->sigma,
                                                    reinterpret_cast<float4*>(ws + w.rowinfo),
-                                                   reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss);
+                                                   reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr, nullptr);
     XB_LAUNCHED();
   }
   {

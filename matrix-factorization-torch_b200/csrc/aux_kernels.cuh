@@ -244,21 +244,29 @@ __device__ __forceinline__ void write_row_losses(int row, int B, float sigma, co
   rowloss[6 * B + row] = w * (lsum2 * LN2 * inv);
 }
 
+// `flag_out` (merged forward + dQ sweep): raised when a partial sum is not finite or a row with negatives sums to
+// zero, i.e. the fixed per-row reference of that sweep was too far from the row's maximum; `cond`: the launch is a
+// no-op unless *cond != 0 (second evaluation after the fallback sweep).
 __global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __restrict__ part, float sigma,
                                  const float4* __restrict__ rowinfo, const float* __restrict__ diag,
-                                 float4* __restrict__ rowstat, float* __restrict__ rowloss) {
+                                 float4* __restrict__ rowstat, float* __restrict__ rowloss, int* __restrict__ flag_out,
+                                 const int* __restrict__ cond) {
+  if (cond != nullptr && *cond == 0) return;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= B) return;
   float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
+  bool bad = false;
   for (int c = 0; c < nchunks; ++c) {
     const float4* p = reinterpret_cast<const float4*>(part + (static_cast<size_t>(c) * nR_pad + row) * 8);
     const float4 a = p[0], b = p[1];
     cnt += a.x; csum += a.y; hsum += a.z; lsum += a.w;
+    bad = bad || !(b.y <= 3.0e38f) || !(fabsf(b.x) <= 3.0e38f);
     if (b.y > 0.f) {
       if (b.x > mx) { se = se * exp2f(mx - b.x) + b.y; mx = b.x; }
       else se += b.y * exp2f(b.x - mx);
     }
   }
+  if (flag_out != nullptr && (bad || (cnt > 0.f && !(se > 0.f)))) atomicOr(flag_out, 1);
   const float lseM2 = se > 0.f ? mx + log2f(se) : -INFINITY;
   write_row_losses(row, B, sigma, rowinfo[row], diag[row], cnt, csum, hsum, lsum, lseM2, rowstat, rowloss);
 }
@@ -342,6 +350,31 @@ __global__ void grad_params_kernel(int B, int lm, const float* __restrict__ u, f
     o[0] = make_float4(g.a2, g.offC, g.kC, g.offI);
     o[1] = make_float4(g.kI, g.offM, g.kM, g.offH);
     o[2] = make_float4(g.kH, g.offL, g.kL, 0.f);
+  }
+}
+
+// Merged forward + dQ sweep (MODE_FWDQ): chunk c left acc_c[i] = sum_j 2^(x_ij - m_ic) v_j and, per column part p,
+// se_icp = sum_j 2^(x_ij - m_ic).  With G_ij = k_i 2^(x_ij + off_i) the gradient pieces are acc_c * f_ic and
+// se_icp * f_ic, f_ic = k_i 2^(m_ic + off_i): rescale in place so that grad_finalize_q_kernel sees what the dQ sweep
+// would have written.  One warp per query row.  No-op when the fallback flag is up (the dQ sweep runs instead).
+__global__ void grad_merge_q_kernel(int B, int nR_pad, int nchunks, int ep, int kp, const float* __restrict__ part,
+                                    const float* __restrict__ qg, float* __restrict__ acc, float* __restrict__ rs,
+                                    const int* __restrict__ flag) {
+  if (*flag != 0) return;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float4 g = reinterpret_cast<const float4*>(qg)[row];   // {a2, off, k, 0}
+  const bool live = g.z != 0.f && fabsf(g.z) <= 3.0e38f && fabsf(g.y) <= 3.0e38f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float m = part[(static_cast<size_t>(c) * ep * nR_pad + row) * 8 + 4];
+    const float f = live ? g.z * exp2f(m + g.y) : 0.f;
+    float* a = acc + (static_cast<size_t>(c) * nR_pad + row) * kp;
+    for (int k = lane; k < kp; k += 32) a[k] = live ? a[k] * f : 0.f;
+    if (lane < ep) {
+      const size_t sub = (static_cast<size_t>(c) * ep + lane) * nR_pad + row;
+      reinterpret_cast<float2*>(rs)[sub] = make_float2(part[sub * 8 + 5] * f, 0.f);
+    }
   }
 }
 

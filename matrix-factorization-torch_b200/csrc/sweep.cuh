@@ -13,6 +13,11 @@
 //   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile written back into TMEM (over the score tile it came
 //              from), followed by a second tcgen05.mma  acc[128 x d] += G[128 x 128] . C_tile[128 x d]
 //              (flash-style recompute).  With (R,C) = (Q,I) acc is dQ; with (R,C) = (I,Q) the same kernel yields dI.
+//   MODE_FWDQ  forward statistics AND the query-side gradient in one sweep (exponential losses): P_ij = 2^(x_ij - m_i)
+//              against a per-row reference m_i fixed after a look at the first tile, se_i = sum_j P_ij (the LSE
+//              statistic), acc_i += P_ij v_j by the second MMA.  The backward pass only rescales acc (flash-attention
+//              forward, with the normalisation postponed); the separate dQ sweep is kept as the fallback for rows whose
+//              sums leave the fp32 range.
 //   MODE_TOPK  epilogue = streaming per-row top-k selection (retrieval, and the semi-hard negative
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
@@ -55,7 +60,7 @@ constexpr bool XB_TRACE_ON = true;
 constexpr bool XB_TRACE_ON = false;
 #endif
 
-enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3 };
+enum SweepMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_TOPK = 2, MODE_DEBUG = 3, MODE_FWDQ = 4 };
 
 // loss bits handled inside the sweep (AlignmentLoss is diagonal-only and never needs a sweep)
 enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 16, LM_ALL = 31 };
@@ -63,7 +68,7 @@ enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 
 __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
 // number of epilogue column parts of a kernel variant
 __host__ __device__ constexpr int epi_parts(int mode, int lm, bool /*qrow*/) {
-  return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
+  return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/ || mode == 4 /*FWDQ*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
 }
 // threads per CTA: epilogue warps + TMA producer warp + two MMA issuer warps
 __host__ __device__ constexpr int sweep_threads(int mode, int lm, bool qrow) { return 96 + 128 * epi_parts(mode, lm, qrow); }
@@ -116,6 +121,7 @@ struct SweepParams {
   float cabs;                // |sigma| * log2(e)
   const float* gsign_src;    // upstream gradient scalar; its sign multiplies the accumulator on the way out
   const uint32_t* csign;     // bit j set <=> column (query) j enters with a negative sign (row sums of G only)
+  const int* cond;           // optional: the launch is a no-op unless *cond != 0 (device-side fallback switch)
 };
 
 struct SweepSmemLayout {
@@ -472,26 +478,30 @@ template <int MODE, int LM, bool QROW, bool LOGQ>
 __global__ void __launch_bounds__(sweep_threads(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
              const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmCa, const SweepParams p) {
-  constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG);
+  constexpr bool FWDQ = (MODE == MODE_FWDQ);
+  constexpr bool HAS_G = (MODE == MODE_GRAD || MODE == MODE_DEBUG || FWDQ);
   constexpr int EP = epi_parts(MODE, LM, QROW);          // epilogue column parts
   constexpr int PW = BN / EP;                            // tile columns owned by one epilogue thread
   constexpr int UW = 16;                                 // columns per unit
   constexpr int UPT = PW / UW;                           // units per thread and tile
   constexpr int EPI_WARPS = 4 * EP;
   constexpr int EPI_THREADS = 128 * EP;
-  constexpr bool EXPFAST = (MODE == MODE_GRAD) && grad_expfast(LM);
+  constexpr bool EXPFAST = (MODE == MODE_GRAD || FWDQ) && grad_expfast(LM);
+  static_assert(!FWDQ || (EXPFAST && QROW), "MODE_FWDQ exists for the query-major sweep of the exponential losses only");
   constexpr bool FOLDED = EXPFAST && !QROW;              // column operand = sign-folded queries (grad_fold_kernel)
   // score-tile buffers in TMEM: without a gradient accumulator all 512 columns hold S tiles, so the MMA thread can
   // run three tiles ahead of the epilogue and the per-tile barrier hand-shakes leave the critical path
   const int NSB = HAS_G ? grad_bufs(p.kp) : 4;
   constexpr int CPAR = (MODE == MODE_GRAD && !QROW) ? grad_qpar_floats(LM) : 2;  // floats per column
+  constexpr int PAR_FLOATS = FWDQ ? 6 : CPAR;     // shared-memory parameter area per column (FWDQ: + 4 x 128 reference exchange)
   constexpr int RPAR = (MODE == MODE_GRAD) ? (QROW ? grad_qpar_floats(LM) : 2) : 4;
 
   // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static smem here)
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (p.cond != nullptr && *p.cond == 0) return;   // fallback launch that is not needed
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const bool aug = p.use_aug != 0;
-  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, aug, CPAR, MODE == MODE_TOPK ? 4 * EP : 0);
+  const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, aug, PAR_FLOATS, MODE == MODE_TOPK ? 4 * EP : 0);
   uint8_t* sR = smem + lay.r_off;
   uint8_t* sC = smem + lay.c_off;
   uint8_t* sRa = smem + lay.ra_off;
@@ -512,7 +522,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const int rb = blockIdx.y;
   const int t_begin = chunk * p.tiles_per_cta;
   const int t_end = min(t_begin + p.tiles_per_cta, p.n_ctiles);
-  const int T = t_end - t_begin;
+  const int T0 = t_end - t_begin;                 // column tiles of this CTA
+  // FWDQ visits its first tile twice: once to fix the row references (G = 0), then for real
+  const int T = (FWDQ && T0 > 0) ? T0 + 1 : T0;
+  auto tile_of = [&](int t) { return t_begin + (FWDQ ? max(t - 1, 0) : t); };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->r_full, 1);
@@ -562,8 +575,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         for (int pt = 0; pt < p.parts; ++pt)
           for (int kb = 0; kb < kb_n; ++kb)
             tma_load_2d(dst + (pt * kb_n + kb) * BLOCK_BYTES, &tmC, &bars->c_full[s], pt * p.kp + kb * KBLK,
-                        (t_begin + t) * BN);
-        if (aug) tma_load_2d(sCa + s * AUG_BYTES, &tmCa, &bars->c_full[s], 16, (t_begin + t) * BN);   // column role
+                        tile_of(t) * BN);
+        if (aug) tma_load_2d(sCa + s * AUG_BYTES, &tmCa, &bars->c_full[s], 16, tile_of(t) * BN);   // column role
       }
     }
   } else if (warp == MMA_WARP || warp == MMA_WARP2) {
@@ -714,7 +727,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
     // lean exponential-gradient path: x = xa * S + xo, result scaled by oscale on the way out
     float xa = 0.f, xo = -300.f, oscale = 1.f;
-    if (EXPFAST) {
+    if (FWDQ) {
+      xa = rp_reg[0];      // a2; the offset -m_i follows from the look-ahead pass
+      xo = 0.f;
+    } else if (EXPFAST) {
       if (QROW) {
         const float k = rp_reg[2];
         const bool live = k != 0.f && fabsf(k) <= 3.0e38f && fabsf(rp_reg[1]) <= 3.0e38f;
@@ -747,7 +763,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // staged column parameters: the item side only carries the LogQ term (the norms ride in the contraction); the
     // query-side gradient blocks of the item-major sweep are staged unless the lean path folded them away
     const bool use_cpar = p.cpar != nullptr &&
-                          ((MODE == MODE_FWD && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED))));
+                          (((MODE == MODE_FWD || FWDQ) && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED))));
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
       if (mrow != nullptr) {
@@ -784,9 +800,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     };
     uint32_t mw0_next = 0u, mw1_next = 0u, sg0_next = 0u, sg1_next = 0u;
     float cpar_next[CSHARE];
-    fetch_mask(t_begin, mw0_next, mw1_next);
-    fetch_cpar(t_begin, cpar_next);
-    fetch_sign(t_begin, sg0_next, sg1_next);
+    fetch_mask(tile_of(0), mw0_next, mw1_next);
+    fetch_cpar(tile_of(0), cpar_next);
+    fetch_sign(tile_of(0), sg0_next, sg1_next);
+    float mrun = -INFINITY;                         // FWDQ: row maximum over this thread's columns of the first tile
 
     // first unit of the first tile.  Units alternate between two register sets (va: even units, vb: odd units), so the
     // load of the next unit lands while the current one is being reduced and nothing is ever copied.
@@ -800,7 +817,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const int b = eb.i;
       const int nb = (b + 1 == NSB) ? 0 : b + 1;                  // next tile's buffer and phase parity
       const uint32_t nph = (b + 1 == NSB) ? (eb.ph ^ 1u) : eb.ph;
-      const int j0 = (t_begin + t) * BN;
+      const int j0 = tile_of(t) * BN;
+      const bool look = FWDQ && t == 0;             // look-ahead pass: row maxima only, G = 0
       const uint32_t buf_addr = tmem_base + lane_off + static_cast<uint32_t>(b * BN) + part_col;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
@@ -813,11 +831,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
       }
       const uint32_t mw0 = mw0_next, mw1 = mw1_next, sg0 = sg0_next, sg1 = sg1_next;
-      if (MODE == MODE_FWD) ucnt += PW - __popc(mw0) - (PW == 64 ? __popc(mw1) : 0);   // unmasked columns of this row
+      if (MODE == MODE_FWD || (FWDQ && !look)) ucnt += PW - __popc(mw0) - (PW == 64 ? __popc(mw1) : 0);   // unmasked columns of this row
       if (t + 1 < T) {
-        fetch_mask(t_begin + t + 1, mw0_next, mw1_next);
-        fetch_cpar(t_begin + t + 1, cpar_next);
-        fetch_sign(t_begin + t + 1, sg0_next, sg1_next);
+        fetch_mask(tile_of(t + 1), mw0_next, mw1_next);
+        fetch_cpar(tile_of(t + 1), cpar_next);
+        fetch_sign(tile_of(t + 1), sg0_next, sg1_next);
       }
       if (use_cpar) named_bar_sync(1, EPI_THREADS);
 
@@ -862,6 +880,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           const float2* colp = reinterpret_cast<const float2*>(cpar_s) + ucol;
           if (__any_sync(0xffffffffu, mu != 0u)) fwd_unit<LM, LOGQ, true>(s, mu, qp, colp, st);
           else fwd_unit<LM, LOGQ, false>(s, mu, qp, colp, st);
+        } else if constexpr (FWDQ) {
+          uint32_t pk[8];
+          const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
+          if (look) {
+            // maximum of the unmasked logits of this unit; the tile's G is all zero
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float x = xa * __uint_as_float(s[c]);
+              if (LOGQ) x -= lqp[c].y;
+              mrun = ((mu >> c) & 1u) ? mrun : fmaxf(mrun, x);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) pk[c] = 0u;
+          } else {
+            float2 us = make_float2(0.f, 0.f);
+            if (__any_sync(0xffffffffu, mu != 0u)) grad_fast_unit<LOGQ, true>(s, mu, xa, xo, lqp, us, pk);
+            else grad_fast_unit<LOGQ, false>(s, mu, xa, xo, lqp, us, pk);
+            rs2 = fadd2(rs2, us);
+          }
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (MODE == MODE_GRAD && EXPFAST) {
           uint32_t pk[8];
           const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
@@ -1064,6 +1102,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->g_full[b]);
       }
+      if (look) {
+        // all column parts of a row feed ONE accumulator row, so they must agree on the reference: the maximum of the
+        // row over the whole first tile (0 if every column of it is masked)
+        float* sref = sPar + 2 * BN;
+        sref[part * BM + row_l] = mrun;
+        named_bar_sync(3, EPI_THREADS);
+        float m = sref[row_l];
+#pragma unroll
+        for (int q = 1; q < EP; ++q) m = fmaxf(m, sref[q * BM + row_l]);
+        mrun = m > -INFINITY ? m : 0.f;
+        xo = -mrun;
+      }
     }
 
     // ----------------------------------------------------------------------- unit epilogue
@@ -1071,6 +1121,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
       o[0] = make_float4(static_cast<float>(ucnt), st.csum, st.hsum, st.lsum);
       o[1] = make_float4(st.mx, st.se, 0.f, 0.f);
+    }
+    if (FWDQ) {
+      // same layout as the forward statistics: (reference, sum of 2^(x - reference)) of this thread's columns
+      float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
+      o[0] = make_float4(static_cast<float>(ucnt), 0.f, 0.f, 0.f);
+      o[1] = make_float4(mrun, rs2.x + rs2.y, 0.f, 0.f);
     }
     if (HAS_G) {
       mbar_wait(&bars->acc_full, 0);
@@ -1092,7 +1148,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
         rgh = 0.f;
       }
-      *reinterpret_cast<float2*>(p.out_stats + out_row * 2) = make_float2(rg, rgh);
+      if (!FWDQ) *reinterpret_cast<float2*>(p.out_stats + out_row * 2) = make_float2(rg, rgh);
     }
     if (MODE == MODE_TOPK) {
       p.cand_cnt[out_row] = cnt;

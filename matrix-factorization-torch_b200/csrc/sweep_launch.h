@@ -13,6 +13,8 @@ cudaError_t launch_sweep_grad_qrow(int lm, bool logq, const CUtensorMap& tmR, co
                                    const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
 cudaError_t launch_sweep_grad_qcol(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                                    const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
+cudaError_t launch_sweep_fwdq(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
+                             const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st);
 cudaError_t launch_sweep_topk(bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa, const SweepParams& p,
                               dim3 grid, size_t smem, cudaStream_t st);
 cudaError_t launch_sweep_debug(const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa, const SweepParams& p, dim3 grid,

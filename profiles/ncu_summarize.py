@@ -14,7 +14,13 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cyc
         "lts__t_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
+traffic = []
 for r in rows[2:]:
+    if "sweep_kernel" in r[idx["Kernel Name"]] and "dram__bytes_read.sum" in idx:
+        def _bytes(name):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[name]]]
+            return float(r[idx[name]].replace(",", "")) * scale
+        traffic.append(_bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum"))
     print("====", r[idx["Kernel Name"]][:90])
     for w in want:
         if w in idx:
@@ -22,6 +28,10 @@ for r in rows[2:]:
     stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     vals = sorted(((float(r[idx[h]].replace(",", "") or 0), h) for h in stall), reverse=True)[:8]
     print("  stalls per issue:", ", ".join(f"{h.split('stalled_')[1].split('_per_')[0]}={v:.2f}" for v, h in vals))
+if traffic and len(sys.argv) > 3:   # third argument: where to write the per-launch DRAM traffic for bench.py
+    import json
+    json.dump({"sweep_dram_bytes_per_launch": sum(traffic) / len(traffic), "launches": len(traffic), "report": rep},
+              open(sys.argv[3], "w"), indent=1)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 kern, cur = [], None
 for r in csv.reader(io.StringIO(src)):
