@@ -390,6 +390,10 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   float* rsi = reinterpret_cast<float*>(ws + w.rsi);
   float* gdiag = reinterpret_cast<float*>(ws + w.gdiag);
   int nq = 1, ni = 1, nq_sub = 1, ni_sub = 1;
+  int n_final_rows = N;   // item rows finished by grad_finalize_i_kernel (the rest are written by the dI sweep itself)
+  const float* fq_part = nullptr;
+  const float* fq_qg = nullptr;
+  const int* fq_flag = nullptr;
   if (lm == 0 || w.mining) {
     XB_CUDA(cudaMemsetAsync(accq, 0, sizeof(float) * static_cast<size_t>(w.B_pad) * w.kp, st));
     XB_CUDA(cudaMemsetAsync(rsq, 0, sizeof(float) * 2 * static_cast<size_t>(w.B_pad), st));
@@ -412,13 +416,10 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     if ((rc = make_aug_map(&tmIa, ws + w.iaug, N))) return rc;
     const bool merged = merged_fwdq(lm, w.mining);
     int* flag = reinterpret_cast<int*>(ws + w.flag);
-    if (merged) {
-      // the forward pass left acc = sum_j 2^(x_ij - m_i) v_j per column chunk: scale it to the gradient
-      grad_merge_q_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
-          B, w.B_pad, w.fq.nchunks, epi_parts(MODE_FWDQ, lm, true), w.kp, reinterpret_cast<const float*>(ws + w.part), qg,
-          accq, rsq, flag);
-      XB_LAUNCHED();
-    }
+    // (merged forward + dQ sweep: acc holds sum_j 2^(x_ij - m_i) v_j per column chunk; grad_finalize_q_kernel scales it)
+    fq_part = merged ? reinterpret_cast<const float*>(ws + w.part) : nullptr;
+    fq_qg = qg;
+    fq_flag = flag;
     {  // dQ sweep: rows = queries, columns = items (with the merged forward: only as its fallback)
       SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
       p.use_aug = 1;
@@ -466,6 +467,15 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
         p.gsign_src = ueff + (lm == LM_INFONCE ? XB_LOSS_INFONCE : XB_LOSS_MINE);
         p.csign = csign;
       }
+      if (w.gi.nchunks == 1) {
+        // one column chunk: item rows beyond the in-batch block get their gradient straight from the sweep
+        p.out_final = di;
+        p.final_v = iprep;
+        p.final_row0 = w.B_pad;
+        p.final_d = d;
+        p.final_dtype = sizeof(T) == 2 ? 1 : 0;
+        n_final_rows = N < w.B_pad ? N : w.B_pad;
+      }
       XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, *tmQc, tmIa, *tmQca, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
@@ -474,10 +484,10 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   }
   grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
       B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
-      dq, gdiag);
+      dq, gdiag, fq_part, fq_qg, fq_flag);
   XB_LAUNCHED();
-  grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(N) * 32, 256), 256, 0, st>>>(
-      N, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
+  grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(n_final_rows) * 32, 256), 256, 0, st>>>(
+      n_final_rows, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
   XB_LAUNCHED();
   return XB_OK;
 }
@@ -633,14 +643,14 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         pq.out_acc = reinterpret_cast<float*>(ws + w.accq);
         XB_SWEEP(launch_sweep_fwdq(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, pq, dim3(w.fq.nchunks, w.fq.n_rblocks),
                                    w.fq.smem, st));
-        loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fq.nchunks * epi_parts(MODE_FWDQ, lm, true), p.out_stats, desc->sigma,
+        loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fq.nchunks * epi_parts(MODE_FWDQ, lm, true), p.out_stats, desc->sigma,
                                                        reinterpret_cast<float4*>(ws + w.rowinfo),
                                                        reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, flag, nullptr);
         XB_LAUNCHED();
         p.cond = flag;
       }
       XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
-      loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
+      loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
                                                      reinterpret_cast<float4*>(ws + w.rowinfo),
                                                      reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr,
                                                      merged ? flag : nullptr);
@@ -675,7 +685,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
     }
   } else {
     // AlignmentLoss only: diagonal terms, no sweep.  An empty partial set gives cnt = 0.
-    loss_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, w.B_pad, 0, nullptr, desc->sigma,
+    loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, w.B_pad, 0, nullptr, desc->sigma,
                                                    reinterpret_cast<float4*>(ws + w.rowinfo),
                                                    reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr, nullptr);
     XB_LAUNCHED();

@@ -252,11 +252,13 @@ __global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __
                                  float4* __restrict__ rowstat, float* __restrict__ rowloss, int* __restrict__ flag_out,
                                  const int* __restrict__ cond) {
   if (cond != nullptr && *cond == 0) return;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per row: lanes take the sub-chunks round-robin, then the (max, sum) pairs merge by shuffles
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (row >= B) return;
   float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
   bool bad = false;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = lane; c < nchunks; c += 32) {
     const float4* p = reinterpret_cast<const float4*>(part + (static_cast<size_t>(c) * nR_pad + row) * 8);
     const float4 a = p[0], b = p[1];
     cnt += a.x; csum += a.y; hsum += a.z; lsum += a.w;
@@ -266,6 +268,21 @@ __global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __
       else se += b.y * exp2f(b.x - mx);
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), ose = __shfl_xor_sync(0xffffffffu, se, o);
+    // merge (mx, se) with (omx, ose) symmetrically so that every lane ends with the same bits
+    const float hi = fmaxf(mx, omx);
+    const float s_mine = se > 0.f ? se * exp2f(mx - hi) : 0.f, s_other = ose > 0.f ? ose * exp2f(omx - hi) : 0.f;
+    se = (mx >= omx) ? s_mine + s_other : s_other + s_mine;
+    mx = hi;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane != 0) return;
   if (flag_out != nullptr && (bad || (cnt > 0.f && !(se > 0.f)))) atomicOr(flag_out, 1);
   const float lseM2 = se > 0.f ? mx + log2f(se) : -INFINITY;
   write_row_losses(row, B, sigma, rowinfo[row], diag[row], cnt, csum, hsum, lsum, lseM2, rowstat, rowloss);
@@ -353,31 +370,6 @@ __global__ void grad_params_kernel(int B, int lm, const float* __restrict__ u, f
   }
 }
 
-// Merged forward + dQ sweep (MODE_FWDQ): chunk c left acc_c[i] = sum_j 2^(x_ij - m_ic) v_j and, per column part p,
-// se_icp = sum_j 2^(x_ij - m_ic).  With G_ij = k_i 2^(x_ij + off_i) the gradient pieces are acc_c * f_ic and
-// se_icp * f_ic, f_ic = k_i 2^(m_ic + off_i): rescale in place so that grad_finalize_q_kernel sees what the dQ sweep
-// would have written.  One warp per query row.  No-op when the fallback flag is up (the dQ sweep runs instead).
-__global__ void grad_merge_q_kernel(int B, int nR_pad, int nchunks, int ep, int kp, const float* __restrict__ part,
-                                    const float* __restrict__ qg, float* __restrict__ acc, float* __restrict__ rs,
-                                    const int* __restrict__ flag) {
-  if (*flag != 0) return;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= B) return;
-  const float4 g = reinterpret_cast<const float4*>(qg)[row];   // {a2, off, k, 0}
-  const bool live = g.z != 0.f && fabsf(g.z) <= 3.0e38f && fabsf(g.y) <= 3.0e38f;
-  for (int c = 0; c < nchunks; ++c) {
-    const float m = part[(static_cast<size_t>(c) * ep * nR_pad + row) * 8 + 4];
-    const float f = live ? g.z * exp2f(m + g.y) : 0.f;
-    float* a = acc + (static_cast<size_t>(c) * nR_pad + row) * kp;
-    for (int k = lane; k < kp; k += 32) a[k] = live ? a[k] * f : 0.f;
-    if (lane < ep) {
-      const size_t sub = (static_cast<size_t>(c) * ep + lane) * nR_pad + row;
-      reinterpret_cast<float2*>(rs)[sub] = make_float2(part[sub * 8 + 5] * f, 0.f);
-    }
-  }
-}
-
 // Operand folding for the item-major gradient sweep of an exponential loss (InfoNCE / MINE, single-loss call).
 // There the tile is rows = items, columns = queries, and G_ij = k_j 2^(a2_j S_ij + off_j [- lq2_i]) with per-QUERY
 // factors.  With c = |sigma| log2 e and s'_j = sign(a2_j):  a2_j S_ij + off_j + log2|k_j| = c (s'_j S_ij + o_j),
@@ -458,15 +450,41 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
                                        const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ ip,
                                        const float* __restrict__ u, float sigma, uint32_t loss_mask,
                                        const float4* __restrict__ rowinfo, const float4* __restrict__ rowstat,
-                                       T* __restrict__ dq, float* __restrict__ gdiag) {
+                                       T* __restrict__ dq, float* __restrict__ gdiag,
+                                       const float* __restrict__ fq_part, const float* __restrict__ fq_qg,
+                                       const int* __restrict__ fq_flag) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
+  // Merged forward + dQ sweep (MODE_FWDQ, fq_part != nullptr and no fallback): chunk c holds acc_c = sum_j 2^(x_ij -
+  // m_ic) v_j and its column parts se_icp = sum_j 2^(x_ij - m_ic); with G_ij = k_i 2^(x_ij + off_i) both scale by
+  // f_ic = k_i 2^(m_ic + off_i).  Otherwise acc / rs_part come from the dQ sweep and f = 1.
+  const bool scaled = fq_part != nullptr && *fq_flag == 0;
+  const int ep = nchunks > 0 ? nsub / nchunks : 1;
+  float fk = 0.f, foff = 0.f;
+  if (scaled) {
+    const float4 g = reinterpret_cast<const float4*>(fq_qg)[row];   // {a2, off, k, 0}
+    const bool live = g.z != 0.f && fabsf(g.z) <= 3.0e38f && fabsf(g.y) <= 3.0e38f;
+    fk = live ? g.z : 0.f;
+    foff = live ? g.y : 0.f;
+  }
+  auto factor = [&](int c) {   // 0 for a dead row: its accumulator may hold inf / NaN from an overflowed reference
+    if (!scaled) return 1.f;
+    return fk != 0.f ? fk * exp2f(fq_part[(static_cast<size_t>(c) * ep * nR_pad + row) * 8 + 4] + foff) : 0.f;
+  };
   float rg = 0.f, rgh = 0.f;
-  for (int c = 0; c < nsub; ++c) {
-    const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);
-    rg += r.x;
-    rgh += r.y;
+  if (scaled) {
+    for (int c = 0; c < nchunks; ++c) {
+      const float f = factor(c);
+      for (int q = 0; q < ep; ++q)
+        if (f != 0.f) rg = fmaf(fq_part[((static_cast<size_t>(c) * ep + q) * nR_pad + row) * 8 + 5], f, rg);
+    }
+  } else {
+    for (int c = 0; c < nsub; ++c) {
+      const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);
+      rg += r.x;
+      rgh += r.y;
+    }
   }
   const float4 ri = rowinfo[row], rst = rowstat[row];
   const float a = sigma * ri.x, w = ri.y, t = ri.z, l2ii = ri.w;
@@ -485,7 +503,10 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int c = 0; c < nchunks; ++c) {
         const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
-        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+        const float f = factor(c);
+        if (f != 0.f) {
+          s.x = fmaf(f, x.x, s.x); s.y = fmaf(f, x.y, s.y); s.z = fmaf(f, x.z, s.z); s.w = fmaf(f, x.w, s.w);
+        }
       }
       const float4 qv = prepped_val4(q, kp, parts, k), vv = prepped_val4(v, kp, parts, k);
       store_out4<T>(dq + static_cast<size_t>(row) * d + k,
@@ -495,7 +516,10 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
   } else {
     for (int k = lane; k < d; k += 32) {
       float s = 0.f;
-      for (int c = 0; c < nchunks; ++c) s += acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k];
+      for (int c = 0; c < nchunks; ++c) {
+        const float f = factor(c);
+        if (f != 0.f) s = fmaf(f, acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k], s);
+      }
       const float qv = prepped_val(q, kp, parts, k), vv = prepped_val(v, kp, parts, k);
       store_out<T>(dq + static_cast<size_t>(row) * d + k, s + gii * vv - cq * qv);
     }

@@ -34,6 +34,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <cstdint>
 
 #include "ptx.cuh"
@@ -122,6 +123,11 @@ struct SweepParams {
   const float* gsign_src;    // upstream gradient scalar; its sign multiplies the accumulator on the way out
   const uint32_t* csign;     // bit j set <=> column (query) j enters with a negative sign (row sums of G only)
   const int* cond;           // optional: the launch is a no-op unless *cond != 0 (device-side fallback switch)
+  // GRAD, item-major sweep with a single column chunk: row blocks at or beyond final_row0 (no in-batch diagonal terms
+  // there) write dI = acc - colsum(G) * v straight from the accumulator instead of the fp32 partials
+  void* out_final;           // [nR][final_d] gradient, final_dtype: 0 = fp32, 1 = bf16; nullptr = always write partials
+  const __nv_bfloat16* final_v;   // the prepared row operand [nR][parts * kp] (hi [, lo]) the colsum term multiplies
+  int final_row0, final_d, final_dtype;
 };
 
 struct SweepSmemLayout {
@@ -1128,7 +1134,70 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       o[0] = make_float4(static_cast<float>(ucnt), 0.f, 0.f, 0.f);
       o[1] = make_float4(mrun, rs2.x + rs2.y, 0.f, 0.f);
     }
-    if (HAS_G) {
+    bool direct = false;
+    if constexpr (MODE == MODE_GRAD && !QROW) direct = p.out_final != nullptr && rb * BM >= p.final_row0;
+    if (HAS_G && direct) {
+      if (EXPFAST) rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
+      // column sum of G for this row = sum over the column parts (one thread each): exchange through shared memory
+      float* sref = sPar;
+      named_bar_sync(3, EPI_THREADS);                 // every warp is done with the staged column parameters
+      sref[part * BM + row_l] = rg;
+      named_bar_sync(3, EPI_THREADS);
+      float cg = 0.f;
+#pragma unroll
+      for (int q = 0; q < EP; ++q) cg += sref[q * BM + row_l];
+      mbar_wait(&bars->acc_full, 0);
+      tc_fence_after();
+      const __nv_bfloat16* vrow = p.final_v + static_cast<size_t>(row_ok ? row : 0) * p.parts * p.kp;
+      for (int cc = part; cc < p.kp / 32; cc += EP) {
+        uint32_t a[32];
+        tmem_ld32(tmem_base + lane_off + acc_col + static_cast<uint32_t>(cc * 32), a);
+        tmem_ld_wait32(a);
+        if (!row_ok || cc * 32 >= p.final_d) continue;
+        float o32[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          const uint4 h = *reinterpret_cast<const uint4*>(vrow + cc * 32 + c);
+          float vv[8] = {__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                         __uint_as_float(h.y & 0xffff0000u), __uint_as_float(h.z << 16), __uint_as_float(h.z & 0xffff0000u),
+                         __uint_as_float(h.w << 16), __uint_as_float(h.w & 0xffff0000u)};
+          if (p.parts == 2) {
+            const uint4 l = *reinterpret_cast<const uint4*>(vrow + p.kp + cc * 32 + c);
+            vv[0] += __uint_as_float(l.x << 16); vv[1] += __uint_as_float(l.x & 0xffff0000u);
+            vv[2] += __uint_as_float(l.y << 16); vv[3] += __uint_as_float(l.y & 0xffff0000u);
+            vv[4] += __uint_as_float(l.z << 16); vv[5] += __uint_as_float(l.z & 0xffff0000u);
+            vv[6] += __uint_as_float(l.w << 16); vv[7] += __uint_as_float(l.w & 0xffff0000u);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float x = __uint_as_float(a[c + u]) * (EXPFAST ? oscale : 1.f);
+            o32[c + u] = x - cg * vv[u];
+          }
+        }
+        const size_t obase = static_cast<size_t>(row) * p.final_d + cc * 32;
+        if (cc * 32 + 32 <= p.final_d && (p.final_d & 7) == 0) {
+          if (p.final_dtype == 1) {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_final) + obase);
+#pragma unroll
+            for (int c = 0; c < 32; c += 8)
+              o[c >> 3] = make_uint4(pack_bf16x2(o32[c], o32[c + 1]), pack_bf16x2(o32[c + 2], o32[c + 3]),
+                                     pack_bf16x2(o32[c + 4], o32[c + 5]), pack_bf16x2(o32[c + 6], o32[c + 7]));
+          } else {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out_final) + obase);
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) o[c >> 2] = make_float4(o32[c], o32[c + 1], o32[c + 2], o32[c + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (cc * 32 + c < p.final_d) {
+              if (p.final_dtype == 1) static_cast<__nv_bfloat16*>(p.out_final)[obase + c] = __float2bfloat16_rn(o32[c]);
+              else static_cast<float*>(p.out_final)[obase + c] = o32[c];
+            }
+          }
+        }
+      }
+    } else if (HAS_G) {
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
       float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
