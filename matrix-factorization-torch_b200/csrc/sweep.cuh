@@ -284,7 +284,11 @@ __device__ __forceinline__ void grad_fast_unit(const uint32_t (&s)[16], uint32_t
       x.x -= cp.y;
       x.y -= cp.w;
     }
+#ifdef XB_DIAG_NOMATH   // timing experiment only: how fast is the sweep when the epilogue math is (nearly) free?
+    const float2 e = x;
+#else
     const float2 e = ex2_pair(x, c >> 1);
+#endif
     float e0 = e.x, e1 = e.y;
     if (MASKED) {
       e0 = ((m16 >> c) & 1u) ? 0.f : e0;
@@ -572,10 +576,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       Ring st;
       for (int t = 0; t < T; ++t, st.advance(NS)) {
         const int s = st.i;
-        const bool tr = XB_TRACE_ON && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < p.trace_tiles;
-        if (tr) p.trace[t * 8 + 6] = clock64();
         mbar_wait(&bars->c_empty[s], st.ph ^ 1u);
-        if (tr) p.trace[t * 8 + 7] = clock64();
         mbar_arrive_expect_tx(&bars->c_full[s], tile_bytes + aug_bytes);
         uint8_t* dst = sC + static_cast<size_t>(s) * tile_bytes;
         for (int pt = 0; pt < p.parts; ++pt)
@@ -768,11 +769,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     const int jl = e_tid & (BN - 1);
     // staged column parameters: the item side only carries the LogQ term (the norms ride in the contraction); the
     // query-side gradient blocks of the item-major sweep are staged unless the lean path folded them away
-    const bool use_cpar = p.cpar != nullptr &&
-                          (((MODE == MODE_FWD || FWDQ) && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED))));
+    constexpr bool use_cpar =
+        ((MODE == MODE_FWD || FWDQ) && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED)));
+    constexpr bool ALWAYS_MASK = (MODE == MODE_FWD || MODE == MODE_GRAD || FWDQ);   // the loss sweeps always carry one
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
-      if (mrow != nullptr) {
+      if (ALWAYS_MASK || mrow != nullptr) {
         if (PW == 64) {
           const uint2 m2 = *reinterpret_cast<const uint2*>(mrow + (jt >> 5) + 2 * part);
           m0 = m2.x;
@@ -798,7 +800,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     auto fetch_sign = [&](int tile, uint32_t& s0, uint32_t& s1) {
       s0 = 0u;
       s1 = 0u;
-      if (FOLDED && p.csign != nullptr) {
+      if (FOLDED) {
         const int w = (tile * BN + PW * part) >> 5;
         s0 = __ldg(p.csign + w);
         if (PW == 64) s1 = __ldg(p.csign + w + 1);
@@ -850,15 +852,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
       auto do_unit = [&](uint32_t (&cur)[UW], uint32_t (&nxt)[UW], const int k) __attribute__((always_inline)) {
         const int ucol = part * PW + k * UW;          // first tile column of this unit
-        // (probe the next tile's score barrier early: the answer is needed only after this unit's load has landed)
-        bool probe = false;
-        if (k + 1 == UPT && t + 1 < T) probe = mbar_try_wait(&bars->s_full[nb], nph);
         // ---- the unit's scores arrive in registers
         tmem_ld_wait_unit<UW>(cur);
         if (tr && k == 0) p.trace[t * 8 + 4] = clock64();
         const uint32_t (&s)[UW] = cur;
-        // ---- start the next unit's load (next tile: hand the buffer back first, and only if its scores are ready)
-        bool pending = false;                          // next tile's first load still to be issued after the math
+        // ---- start the next unit's load (next tile: hand this tile's buffer back first).  The MMA warps run ahead of
+        // the epilogue, so the wait for the next tile's scores is normally a single successful try_wait.
         if (k + 1 < UPT) {
           tmem_ld_unit<UW>(buf_addr + static_cast<uint32_t>((k + 1) * UW), nxt);
         } else {
@@ -868,13 +867,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             if (lane == 0) mbar_arrive(&bars->s_empty[b]);
           }
           if (t + 1 < T) {
-            const bool ready = __all_sync(0xffffffffu, probe);
-            if (ready) {
-              tc_fence_after();
-              tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
-            } else {
-              pending = true;
-            }
+            mbar_wait(&bars->s_full[nb], nph);
+            tc_fence_after();
+            tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
           }
         }
         // ---- the unit's math
@@ -1087,12 +1082,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             }
           }
         }
-        // ---- the next tile's scores were not ready before the math: wait for them now
-        if (pending) {
-          mbar_wait(&bars->s_full[nb], nph);
-          tc_fence_after();
-          tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
-        }
+        if (tr && k == 0) p.trace[t * 8 + 7] = clock64();
       };
       static_assert((UPT & 1) == 0, "units per tile must be even (register ping-pong)");
 #pragma unroll
@@ -1107,6 +1097,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->g_full[b]);
+        if (tr) p.trace[t * 8 + 6] = clock64();
       }
       if (look) {
         // all column parts of a row feed ONE accumulator row, so they must agree on the reference: the maximum of the

@@ -42,7 +42,9 @@ def show(nm, lo, hi):
     d = (t[hi - 1, 5] - t[lo, 5]).item() / (hi - 1 - lo)
     print(f"{nm}: period {d:.0f}; epi: s_full wait {float((t[lo:hi, 4] - t[lo:hi, 3]).float().mean()):.0f} busy {float((t[lo:hi, 5] - t[lo:hi, 4]).float().mean()):.0f};"
           f" mma: s_empty wait {float((t[lo:hi, 1] - t[lo:hi, 0]).float().mean()):.0f} c_full wait {float((t[lo:hi, 2] - t[lo:hi, 1]).float().mean()):.0f}"
-          f" issue+rest {float((t[lo + 1:hi + 1, 0] - t[lo:hi, 2]).float().mean()):.0f}; producer c_empty wait {float((t[lo:hi, 7] - t[lo:hi, 6]).float().mean()):.0f}")
+          f" issue+rest {float((t[lo + 1:hi + 1, 0] - t[lo:hi, 2]).float().mean()):.0f};"
+          f" epi detail: unit0 {float((t[lo:hi, 7] - t[lo:hi, 4]).float().mean()):.0f} unit1 {float((t[lo:hi, 5] - t[lo:hi, 7]).float().mean()):.0f}"
+          f" st_wait+arrive {float((t[lo:hi, 6] - t[lo:hi, 5]).float().mean()):.0f} next-tile-top {float((t[lo + 1:hi + 1, 3] - t[lo:hi, 6]).float().mean()):.0f}")
 _lib.lib.xb_debug_set_trace(trace.data_ptr(), NT)
 xfmr_b200.topk_search(q, items, 100); torch.cuda.synchronize()
 _lib.lib.xb_debug_set_trace(None, 0)
