@@ -196,7 +196,7 @@ static inline int sweep_lm_from_mask(uint32_t loss_mask) {
 // Pair mask
 // ------------------------------------------------------------------------------------------------
 struct PairMaskWs {
-  size_t keys_off, heads_off, next_off, total;
+  size_t keys_off, cnt_off, fill_off, start_off, slot_of_off, cols_off, cursor_off, total;
   int tsize;
 };
 static PairMaskWs pair_mask_ws(int ncols) {
@@ -204,10 +204,15 @@ static PairMaskWs pair_mask_ws(int ncols) {
   int ts = 64;
   while (ts < 2 * ncols) ts <<= 1;
   w.tsize = ts;
+  const size_t nc = ncols > 0 ? ncols : 1;
   size_t off = 0;
   w.keys_off = off; off = align_up(off + sizeof(long long) * ts, 256);
-  w.heads_off = off; off = align_up(off + sizeof(int) * ts, 256);
-  w.next_off = off; off = align_up(off + sizeof(int) * (ncols > 0 ? ncols : 1), 256);
+  w.cnt_off = off; off = align_up(off + sizeof(int) * ts, 256);
+  w.fill_off = off; off = align_up(off + sizeof(int) * ts, 256);
+  w.start_off = off; off = align_up(off + sizeof(int) * ts, 256);
+  w.slot_of_off = off; off = align_up(off + sizeof(int) * nc, 256);
+  w.cols_off = off; off = align_up(off + sizeof(int) * nc, 256);
+  w.cursor_off = off; off = align_up(off + sizeof(int) * 4, 256);
   w.total = off;
   return w;
 }
@@ -217,8 +222,12 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
                            cudaStream_t st) {
   const PairMaskWs w = pair_mask_ws(ncols);
   long long* keys = reinterpret_cast<long long*>(ws + w.keys_off);
-  int* heads = reinterpret_cast<int*>(ws + w.heads_off);
-  int* next = reinterpret_cast<int*>(ws + w.next_off);
+  int* cnt = reinterpret_cast<int*>(ws + w.cnt_off);
+  int* fill = reinterpret_cast<int*>(ws + w.fill_off);
+  int* start = reinterpret_cast<int*>(ws + w.start_off);
+  int* slot_of = reinterpret_cast<int*>(ws + w.slot_of_off);
+  int* cols = reinterpret_cast<int*>(ws + w.cols_off);
+  int* cursor = reinterpret_cast<int*>(ws + w.cursor_off);
   const int words = mask_words_for(ncols), words_t = mask_words_for(nrows);
   const int rows_pad = cdiv(nrows, BM) * BM, cols_pad = cdiv(ncols, BM) * BM;
   {
@@ -231,13 +240,17 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
   }
   const bool any_ids = (row_ids0 != nullptr) || (row_lists != nullptr && list_len > 0);
   if (!any_ids || ncols == 0 || nrows == 0) return XB_OK;
-  hash_clear_kernel<<<cdiv(w.tsize, 256), 256, 0, st>>>(keys, heads, w.tsize);
+  hash_clear_kernel<<<cdiv(w.tsize, 256), 256, 0, st>>>(keys, cnt, fill, cursor, w.tsize);
   XB_LAUNCHED();
-  hash_insert_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(col_ids, ncols, keys, heads, next, w.tsize - 1);
+  hash_insert_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(col_ids, ncols, keys, cnt, slot_of, w.tsize - 1);
+  XB_LAUNCHED();
+  hash_offsets_kernel<<<cdiv(w.tsize, 256), 256, 0, st>>>(cnt, start, cursor, w.tsize);
+  XB_LAUNCHED();
+  hash_fill_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(ncols, slot_of, start, fill, cols);
   XB_LAUNCHED();
   const int ll = (row_lists != nullptr) ? list_len : 0;
   const long long threads = static_cast<long long>(nrows) * (ll + 1);
-  hash_mark_kernel<<<cdiv(threads, 256), 256, 0, st>>>(nrows, ll, row_ids0, row_lists, keys, heads, next, w.tsize - 1,
+  hash_mark_kernel<<<cdiv(threads, 256), 256, 0, st>>>(nrows, ll, row_ids0, row_lists, keys, cnt, start, cols, w.tsize - 1,
                                                        mask, words, mask_t, words_t);
   XB_LAUNCHED();
   return XB_OK;

@@ -161,15 +161,23 @@ __device__ __forceinline__ uint32_t hash64(long long id) {
   return static_cast<uint32_t>(x);
 }
 
-__global__ void hash_clear_kernel(long long* __restrict__ keys, int* __restrict__ heads, int tsize) {
+// Hash table over the column ids: open addressing on the 64-bit id; every slot owns a CONTIGUOUS run of the column
+// indices that carry its id (cols[start[slot] .. start[slot] + cnt[slot])).  Popular ids occur hundreds of times in a
+// Zipf-distributed batch; contiguous runs keep the marking loop free of dependent loads (a linked list costs one L2
+// round trip per element).  Four small launches: clear, insert + count, run offsets (atomic bump, order is
+// irrelevant), fill.
+__global__ void hash_clear_kernel(long long* __restrict__ keys, int* __restrict__ cnt, int* __restrict__ fill,
+                                  int* __restrict__ cursor, int tsize) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *cursor = 0;
   if (i >= tsize) return;
   keys[i] = EMPTY_KEY;
-  heads[i] = -1;
+  cnt[i] = 0;
+  fill[i] = 0;
 }
 
 __global__ void hash_insert_kernel(const long long* __restrict__ col_ids, int ncols, long long* keys,
-                                   int* heads, int* __restrict__ next, int tmask) {
+                                   int* __restrict__ cnt, int* __restrict__ slot_of, int tmask) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ncols) return;
   const long long id = col_ids[j];
@@ -181,14 +189,42 @@ __global__ void hash_insert_kernel(const long long* __restrict__ col_ids, int nc
     if (prev == EMPTY_KEY || prev == id) break;
     slot = (slot + 1) & tmask;
   }
-  next[j] = atomicExch(heads + slot, j);
+  atomicAdd(cnt + slot, 1);
+  slot_of[j] = static_cast<int>(slot);
+}
+
+__global__ void hash_offsets_kernel(const int* __restrict__ cnt, int* __restrict__ start, int* __restrict__ cursor,
+                                    int tsize) {
+  // one atomic per warp: lanes scan their counts, the last lane reserves the warp's total
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = i < tsize ? cnt[i] : 0;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  int base = 0;
+  if (lane == 31 && incl > 0) base = atomicAdd(cursor, incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (c > 0) start[i] = base + incl - c;
+}
+
+__global__ void hash_fill_kernel(int ncols, const int* __restrict__ slot_of, const int* __restrict__ start,
+                                 int* __restrict__ fill, int* __restrict__ cols) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  const int slot = slot_of[j];
+  cols[start[slot] + atomicAdd(fill + slot, 1)] = j;
 }
 
 // one thread per (row, list entry); entry index list_len stands for row_ids0[row]
 __global__ void hash_mark_kernel(int nrows, int list_len, const long long* __restrict__ row_ids0,
                                  const long long* __restrict__ row_lists, const long long* __restrict__ keys,
-                                 const int* __restrict__ heads, const int* __restrict__ next, int tmask,
-                                 uint32_t* mask, int words, uint32_t* mask_t, int words_t) {
+                                 const int* __restrict__ cnt, const int* __restrict__ start,
+                                 const int* __restrict__ cols, int tmask, uint32_t* mask, int words, uint32_t* mask_t,
+                                 int words_t) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per_row = list_len + 1;
   if (gid >= static_cast<long long>(nrows) * per_row) return;
@@ -209,9 +245,15 @@ __global__ void hash_mark_kernel(int nrows, int list_len, const long long* __res
     if (k == id) break;
     slot = (slot + 1) & tmask;
   }
-  for (int c = heads[slot]; c >= 0; c = next[c]) {
-    atomicOr(mask + static_cast<size_t>(r) * words + (c >> 5), 1u << (c & 31));
-    if (mask_t != nullptr) atomicOr(mask_t + static_cast<size_t>(c) * words_t + (r >> 5), 1u << (r & 31));
+  const int n = cnt[slot];
+  const int* run = cols + start[slot];
+  uint32_t* mrow = mask + static_cast<size_t>(r) * words;
+  const uint32_t rbit = 1u << (r & 31);
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const int c = run[i];
+    atomicOr(mrow + (c >> 5), 1u << (c & 31));
+    if (mask_t != nullptr) atomicOr(mask_t + static_cast<size_t>(c) * words_t + (r >> 5), rbit);
   }
 }
 
@@ -468,17 +510,24 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
     fk = live ? g.z : 0.f;
     foff = live ? g.y : 0.f;
   }
-  auto factor = [&](int c) {   // 0 for a dead row: its accumulator may hold inf / NaN from an overflowed reference
+  auto factor_of = [&](int c) {   // 0 for a dead row: its accumulator may hold inf / NaN from an overflowed reference
     if (!scaled) return 1.f;
     return fk != 0.f ? fk * exp2f(fq_part[(static_cast<size_t>(c) * ep * nR_pad + row) * 8 + 4] + foff) : 0.f;
   };
+  // the usual case (<= 32 column chunks): lane c keeps chunk c's factor, the loops below fetch it with a shuffle
+  const bool by_lane = nchunks <= 32;
+  const float fac_lane = (by_lane && lane < nchunks) ? factor_of(lane) : 0.f;
+  auto factor = [&](int c) { return by_lane ? __shfl_sync(0xffffffffu, fac_lane, c) : factor_of(c); };
   float rg = 0.f, rgh = 0.f;
   if (scaled) {
-    for (int c = 0; c < nchunks; ++c) {
-      const float f = factor(c);
-      for (int q = 0; q < ep; ++q)
-        if (f != 0.f) rg = fmaf(fq_part[((static_cast<size_t>(c) * ep + q) * nR_pad + row) * 8 + 5], f, rg);
+    // lanes split the (chunk, part) pairs, then a warp sum
+    for (int s0 = 0; s0 < nsub; s0 += 32) {   // (uniform trip count: every lane takes part in the shuffle)
+      const int s = min(s0 + lane, nsub - 1);
+      const float f = by_lane ? __shfl_sync(0xffffffffu, fac_lane, s / ep) : factor_of(s / ep);
+      if (s0 + lane < nsub && f != 0.f) rg = fmaf(fq_part[(static_cast<size_t>(s) * nR_pad + row) * 8 + 5], f, rg);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rg += __shfl_xor_sync(0xffffffffu, rg, o);
   } else {
     for (int c = 0; c < nsub; ++c) {
       const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);
