@@ -509,6 +509,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static smem here)
   extern __shared__ __align__(1024) uint8_t smem[];
   if (p.cond != nullptr && *p.cond == 0) return;   // fallback launch that is not needed
+  const bool ctr = XB_TRACE_ON && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  if (ctr) p.trace[p.trace_tiles * 8 + 0] = clock64();
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const bool aug = p.use_aug != 0;
   const SweepSmemLayout lay = sweep_smem_layout(p.kp, p.parts, p.nstages, aug, PAR_FLOATS, MODE == MODE_TOPK ? 4 * EP : 0);
@@ -563,6 +565,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (ctr) p.trace[p.trace_tiles * 8 + 1] = clock64();
 
   if (warp == PRODUCER_WARP) {
     // ======================================================================== TMA producer
@@ -817,6 +820,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // load of the next unit lands while the current one is being reduced and nothing is ever copied.
     uint32_t va[UW], vb[UW];
     mbar_wait(&bars->s_full[0], 0);
+    if (ctr) p.trace[p.trace_tiles * 8 + 2] = clock64();
     tc_fence_after();
     tmem_ld_unit<UW>(tmem_base + lane_off + part_col, va);
 
@@ -1114,6 +1118,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
 
     // ----------------------------------------------------------------------- unit epilogue
+    if (ctr) p.trace[p.trace_tiles * 8 + 3] = clock64();
     if (MODE == MODE_FWD) {
       float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
       o[0] = make_float4(static_cast<float>(ucnt), st.csum, st.hsum, st.lsum);
@@ -1215,9 +1220,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
   }
 
+  if (ctr) p.trace[p.trace_tiles * 8 + 4] = clock64();
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (ctr) p.trace[p.trace_tiles * 8 + 5] = clock64();
   if (warp == MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 

@@ -56,3 +56,7 @@ trace.zero_()
 loss.backward(); torch.cuda.synchronize()
 _lib.lib.xb_debug_set_trace(None, 0)
 show("GRAD dI", 16, 28)
+t = trace.cpu()
+c = t[77]
+print(f"GRAD dI CTA(0,0) phases (cycles): launch->setup done {int(c[1]-c[0])}, ->first scores {int(c[2]-c[1])}, main loop {int(c[3]-c[2])},"
+      f" accumulator write-out {int(c[4]-c[3])}, final sync {int(c[5]-c[4])}; tiles 0..31 ends:", [int(x - c[2]) for x in t[0:32:4, 5]])
