@@ -489,7 +489,15 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
         p.final_dtype = sizeof(T) == 2 ? 1 : 0;
         n_final_rows = N < w.B_pad ? N : w.B_pad;
       }
-      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, *tmQc, tmIa, *tmQca, p, dim3(w.gi.nchunks, w.gi.n_rblocks),
+      // persistent launch: one CTA per SM walks the item row blocks (685 of them at config 2), so the pipeline never drains
+      static const bool persist = [] {
+        const char* e = std::getenv("XB_PERSIST");
+        return e == nullptr || e[0] != '0';
+      }();
+      int gy = w.gi.n_rblocks;
+      const int per_chunk = NUM_SMS / (w.gi.nchunks > 0 ? w.gi.nchunks : 1);
+      if (persist && per_chunk >= 1 && gy > per_chunk) gy = per_chunk;
+      XB_SWEEP(launch_sweep_grad_qcol(lm, desc->has_log_q != 0, tmI, *tmQc, tmIa, *tmQca, p, dim3(w.gi.nchunks, gy),
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
       ni_sub = ni * epi_parts(MODE_GRAD, lm, false);

@@ -160,6 +160,8 @@ struct SweepBars {
   uint64_t s_empty[4];   // FWD / TOPK: epilogue -> MMA (one arrival per epilogue warp)
   uint64_t g_full[4];    // GRAD: G tile written (one arrival per epilogue warp)
   uint64_t acc_full;
+  uint64_t r_empty;      // persistent launches: every score MMA of a row block has read the resident row tile
+  uint64_t acc_empty;    // persistent launches: the epilogue has read the accumulator of a row block
   uint32_t tmem_base;
 };
 static_assert(sizeof(SweepBars) <= 256, "barrier area overflow");
@@ -531,7 +533,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const uint32_t acc_col = static_cast<uint32_t>(grad_bufs(p.kp)) * BN;   // TMEM columns of the gradient accumulator
 
   const int chunk = blockIdx.x;
-  const int rb = blockIdx.y;
+  // A CTA walks the row blocks rb0, rb0 + gridDim.y, ...  The usual launch has one row block per CTA; the item-major
+  // gradient sweep is launched persistent (gridDim.y = #SMs): its tile pipeline (stage ring, TMEM ring, prefetched
+  // tcgen05.ld) runs on across row blocks, so set-up, the first loads and the accumulator write-out of one block hide
+  // behind the MMAs of the next.
+  const int rb0 = blockIdx.y;
+  const int rb_step = gridDim.y;
+  const int n_rblocks = p.nR_pad / BM;
   const int t_begin = chunk * p.tiles_per_cta;
   const int t_end = min(t_begin + p.tiles_per_cta, p.n_ctiles);
   const int T0 = t_end - t_begin;                 // column tiles of this CTA
@@ -551,6 +559,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       mbar_init(&bars->g_full[b], EPI_WARPS);
     }
     mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->r_empty, 1);
+    mbar_init(&bars->acc_empty, EPI_WARPS);
     fence_barrier_init();
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmC);
@@ -571,12 +581,15 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // ======================================================================== TMA producer
     if (lane == 0 && T > 0) {
       const uint32_t aug_bytes = aug ? AUG_BYTES : 0u;
+      Ring st;
+      int blk = 0;
+      for (int rb = rb0; rb < n_rblocks; rb += rb_step, ++blk) {
+      if (blk > 0) mbar_wait(&bars->r_empty, (blk - 1) & 1);   // the previous block's score MMAs are done with sR
       mbar_arrive_expect_tx(&bars->r_full, tile_bytes + aug_bytes);
       for (int pt = 0; pt < p.parts; ++pt)
         for (int kb = 0; kb < kb_n; ++kb)
           tma_load_2d(sR + (pt * kb_n + kb) * BLOCK_BYTES, &tmR, &bars->r_full, pt * p.kp + kb * KBLK, rb * BM);
       if (aug) tma_load_2d(sRa, &tmRa, &bars->r_full, 0, rb * BM);              // row-role columns [0,16)
-      Ring st;
       for (int t = 0; t < T; ++t, st.advance(NS)) {
         const int s = st.i;
         mbar_wait(&bars->c_empty[s], st.ph ^ 1u);
@@ -587,6 +600,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             tma_load_2d(dst + (pt * kb_n + kb) * BLOCK_BYTES, &tmC, &bars->c_full[s], pt * p.kp + kb * KBLK,
                         tile_of(t) * BN);
         if (aug) tma_load_2d(sCa + s * AUG_BYTES, &tmCa, &bars->c_full[s], 16, tile_of(t) * BN);   // column role
+      }
       }
     }
   } else if (warp == MMA_WARP || warp == MMA_WARP2) {
@@ -683,17 +697,25 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
         }
       } else if (!second) {
-        mbar_wait(&bars->r_full, 0);
-        for (int t = 0; t < T; ++t) {
-          issue_scores(t);
-          sb.advance(NSB);
-          ss.advance(NS);
+        int blk = 0;
+        for (int rb = rb0; rb < n_rblocks; rb += rb_step, ++blk) {
+          mbar_wait(&bars->r_full, blk & 1);
+          for (int t = 0; t < T; ++t) {
+            issue_scores(t);
+            sb.advance(NSB);
+            ss.advance(NS);
+          }
+          if (elect_one()) umma_commit(&bars->r_empty);   // sR may be overwritten once these MMAs have run
+          __syncwarp();
         }
       } else {
+        int blk = 0;
+        for (int rb = rb0; rb < n_rblocks; rb += rb_step, ++blk) {
         for (int t = 0; t < T; ++t, sb.advance(NSB), ss.advance(NS)) {
           const int s = ss.i;
           const int b = sb.i;
           mbar_wait(&bars->g_full[b], sb.ph);
+          if (t == 0 && blk > 0) mbar_wait(&bars->acc_empty, (blk - 1) & 1);   // previous block's accumulator was read
           tc_fence_after();
           if (elect_one()) {
             // acc[128 x kp] += G[128 x 128] . C_tile[128 x kp]: A = G from TMEM (K-step kk = 8 packed columns at
@@ -716,6 +738,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
         if (elect_one()) umma_commit(&bars->acc_full);
         __syncwarp();
+        }
       }
     }
   } else if (T > 0) {
@@ -724,6 +747,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     const int part = warp >> 2;                     // column part of the tile this warp reduces
     const int row_l = quad * 32 + lane;             // tile row == TMEM lane
     const int e_tid = threadIdx.x;                  // 0..EPI_THREADS-1, used for cooperative parameter loads
+    uint32_t va[UW], vb[UW];                        // unit registers (even / odd units), see below
+    Ring eb;                                        // TMEM buffer ring of the epilogue (runs on across row blocks)
+    int blk = 0;
+    for (int rb = rb0; rb < n_rblocks; rb += rb_step, ++blk) {
+    const bool more_blocks = rb + rb_step < n_rblocks;
     const int row = rb * BM + row_l;
     const bool row_ok = row < p.nR;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -818,13 +846,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
     // first unit of the first tile.  Units alternate between two register sets (va: even units, vb: odd units), so the
     // load of the next unit lands while the current one is being reduced and nothing is ever copied.
-    uint32_t va[UW], vb[UW];
-    mbar_wait(&bars->s_full[0], 0);
-    if (ctr) p.trace[p.trace_tiles * 8 + 2] = clock64();
-    tc_fence_after();
-    tmem_ld_unit<UW>(tmem_base + lane_off + part_col, va);
+    if (blk == 0) {   // (later blocks: the last tile of the previous block has already issued this load)
+      mbar_wait(&bars->s_full[0], 0);
+      if (ctr) p.trace[p.trace_tiles * 8 + 2] = clock64();
+      tc_fence_after();
+      tmem_ld_unit<UW>(tmem_base + lane_off + part_col, va);
+    }
 
-    Ring eb;   // TMEM buffer ring of the epilogue
     for (int t = 0; t < T; ++t, eb.advance(NSB)) {
       const int b = eb.i;
       const int nb = (b + 1 == NSB) ? 0 : b + 1;                  // next tile's buffer and phase parity
@@ -870,7 +898,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->s_empty[b]);
           }
-          if (t + 1 < T) {
+          if (t + 1 < T || more_blocks) {   // (the first tile of the next row block follows in the same rings)
             mbar_wait(&bars->s_full[nb], nph);
             tc_fence_after();
             tmem_ld_unit<UW>(tmem_base + lane_off + static_cast<uint32_t>(nb * BN) + part_col, nxt);
@@ -1142,7 +1170,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       float cg = 0.f;
 #pragma unroll
       for (int q = 0; q < EP; ++q) cg += sref[q * BM + row_l];
-      mbar_wait(&bars->acc_full, 0);
+      mbar_wait(&bars->acc_full, blk & 1);
       tc_fence_after();
       const __nv_bfloat16* vrow = p.final_v + static_cast<size_t>(row_ok ? row : 0) * p.parts * p.kp;
       for (int cc = part; cc < p.kp / 32; cc += EP) {
@@ -1194,7 +1222,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
       }
     } else if (HAS_G) {
-      mbar_wait(&bars->acc_full, 0);
+      mbar_wait(&bars->acc_full, blk & 1);
       tc_fence_after();
       float* o = p.out_acc + (static_cast<size_t>(chunk) * p.nR_pad + row) * p.kp;
       for (int cc = part; cc < p.kp / 32; cc += EP) {   // accumulator chunks are dealt round-robin to the parts
@@ -1218,6 +1246,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     if (MODE == MODE_TOPK) {
       p.cand_cnt[out_row] = cnt;
     }
+    if (HAS_G && more_blocks) {
+      // the accumulator is in registers / memory: the second MMA of the next row block may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty);
+    }
+    }   // row blocks
   }
 
   if (ctr) p.trace[p.trace_tiles * 8 + 4] = clock64();

@@ -52,11 +52,12 @@ show("TOPK", 3000, 3012)
 trace.zero_(); _lib.lib.xb_debug_set_trace(trace.data_ptr(), 77)
 loss = fwd(); torch.cuda.synchronize()
 show("FWD", 40, 52)
-trace.zero_()
+trace.zero_(); _lib.lib.xb_debug_set_trace(trace.data_ptr(), 200)
 loss.backward(); torch.cuda.synchronize()
 _lib.lib.xb_debug_set_trace(None, 0)
 show("GRAD dI", 16, 28)
-t = trace.cpu()
-c = t[77]
-print(f"GRAD dI CTA(0,0) phases (cycles): launch->setup done {int(c[1]-c[0])}, ->first scores {int(c[2]-c[1])}, main loop {int(c[3]-c[2])},"
-      f" accumulator write-out {int(c[4]-c[3])}, final sync {int(c[5]-c[4])}; tiles 0..31 ends:", [int(x - c[2]) for x in t[0:32:4, 5]])
+tt = trace.cpu()
+print("GRAD dI tile-end stamps of CTA(0,0), every 8th of the last block's tiles:", [int(x - tt[0, 3]) for x in tt[0:32:4, 5]])
+c = tt[200]
+print(f"GRAD dI CTA(0,0): launch->setup {int(c[1]-c[0])}, ->first scores {int(c[2]-c[1])}, to last block's loop end {int(c[3]-c[2])}, last write-out {int(c[4]-c[3])}, total {int(c[5]-c[0])}")
+
