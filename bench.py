@@ -465,7 +465,8 @@ def main() -> None:  # noqa: PLR0915
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": ncu_traffic(),
-            "kernel": "xb::sweep_kernel (3 launches per step: loss statistics, dQ, dI)",
+            "kernel": "xb::sweep_kernel (2 working launches per step: merged forward + dQ sweep, dI sweep; plus 2 conditional "
+                      "fallback launches that exit at once)",
             "algorithmic_flops_per_step": algo_flops, "sweep_ms_per_step": sweep_ms_per_step,
             "sweep_launches_per_step": sweep_count / args.steps, "peak_source": pk["source"] + " sustained bf16",
             "sweep_share_of_step": sweep_ms_per_step / ms_per_step,

@@ -16,7 +16,9 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cyc
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
 traffic = []
 for r in rows[2:]:
-    if "sweep_kernel" in r[idx["Kernel Name"]] and "dram__bytes_read.sum" in idx:
+    # (the conditional fallback launches of the merged sweep exit at once: only launches that did work count)
+    if ("sweep_kernel" in r[idx["Kernel Name"]] and "dram__bytes_read.sum" in idx
+            and float(r[idx["gpu__time_duration.sum"]].replace(",", "")) > 20.0):
         def _bytes(name):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[name]]]
             return float(r[idx[name]].replace(",", "")) * scale
