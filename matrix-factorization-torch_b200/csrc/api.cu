@@ -145,7 +145,9 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
   SweepPlan pl{};
   pl.n_rblocks = cdiv(nR, BM);
   pl.n_ctiles = cdiv(nC, BN);
-  int want = (2 * NUM_SMS) / (pl.n_rblocks > 0 ? pl.n_rblocks : 1);
+  // loss sweeps: ~2 CTAs per SM.  Selection sweeps (top-k, mining): every column chunk of a row is a separate
+  // candidate stream that starts with an open threshold, so take as few chunks as fill the machine once.
+  int want = ((topk_warps > 0 ? 1 : 2) * NUM_SMS) / (pl.n_rblocks > 0 ? pl.n_rblocks : 1);
   if (want < 1) want = 1;
   if (want > pl.n_ctiles) want = pl.n_ctiles;
   if (want < 1) want = 1;
@@ -259,7 +261,13 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
 // ------------------------------------------------------------------------------------------------
 // Loss workspace
 // ------------------------------------------------------------------------------------------------
-constexpr int MINE_CAP = 256;    // candidate buffer per row for the mining sweep
+constexpr int MINE_CAP = 256;    // largest candidate buffer per row for the mining sweep (workspace is sized for it)
+// actual buffer for a given number of kept entries
+static int mine_cap_for(int keep) {
+  int cap = 64;
+  while (cap < 8 * keep + 32) cap <<= 1;   // (measured: compactions cost more than the candidates a fresher threshold saves)
+  return cap < MINE_CAP ? cap : MINE_CAP;
+}
 constexpr int MINE_KMAX = 64;    // largest supported num_negatives
 constexpr int MINE_OVERFETCH = 16;  // extra candidates per side re-scored exactly before the final selection
 
@@ -682,13 +690,13 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.rpar = reinterpret_cast<float*>(ws + w.qmine);
       p.cand = reinterpret_cast<unsigned long long*>(ws + w.cand);
       p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
-      p.cap = MINE_CAP;
+      p.cap = mine_cap_for(w.Kf);
       p.keep = w.Kf;
       for (int side = 0; side < 2; ++side) {
         p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
-            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), MINE_CAP, w.Kf, p.cand, p.cand_cnt,
+            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), p.cap, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
         XB_LAUNCHED();
       }
