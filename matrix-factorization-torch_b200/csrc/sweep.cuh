@@ -1048,7 +1048,27 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             hit = kmax > thr;
           }
           uint32_t hm = __ballot_sync(0xffffffffu, hit);
-          if (hm) {
+          if (MINING && hm) {
+            // mining sweeps are all warm-up (few columns per row): most rows of a warp hit in most units.  Every lane
+            // parks its 16 keys in shared memory (dynamic indexing), builds the bit mask of its passing columns and
+            // appends them to its OWN row's buffer - the cost does not grow with the number of rows that hit.
+            uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(mine + q4 * 4) = make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
+            uint32_t pm = 0u;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pm |= (w[c] > thr) ? (1u << c) : 0u;
+            pm &= ~mu;
+            unsigned long long* cb = p.cand + out_row * p.cap;
+            const uint32_t col0 = static_cast<uint32_t>(j0 + ucol);
+            while (pm) {
+              const int c = __ffs(pm) - 1;
+              pm &= pm - 1;
+              cb[cnt++] = (static_cast<unsigned long long>(mine[c]) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+            }
+            __syncwarp();
+          } else if (hm) {
             uint32_t* stg = sStage + (warp * 32) * TOPK_STAGE_STRIDE;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
