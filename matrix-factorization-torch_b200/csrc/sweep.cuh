@@ -1004,9 +1004,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
           tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (MODE == MODE_TOPK) {
-          // Streaming selection.  Fast path: one 3-input max per two elements against the row's threshold.  A unit in
-          // which some row can beat its current k-th best is staged in shared memory and the hit rows are then scanned
-          // two at a time, one per half-warp (ballot + popc-compacted appends) - rows hit rarely, warps hit often.
+          // Streaming selection.  Fast path: one 3-input max per two elements against the row's threshold and one warp
+          // vote; a unit in which some row can beat its current k-th best takes the append path below.
           constexpr bool MINING = LM != 0;
           uint32_t w[16];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
           bool hit;
@@ -1048,89 +1047,47 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             hit = kmax > thr;
           }
           uint32_t hm = __ballot_sync(0xffffffffu, hit);
-          if (MINING && hm) {
-            // mining sweeps are all warm-up (few columns per row): most rows of a warp hit in most units.  Every lane
-            // parks its 16 keys in shared memory (dynamic indexing), builds the bit mask of its passing columns and
-            // appends them to its OWN row's buffer - the cost does not grow with the number of rows that hit.
+          if (hm) {
+            // Every lane parks its 16 words in shared memory (dynamic indexing), builds the bit mask of its passing
+            // columns and appends them to its OWN row's buffer: no shuffles, and the cost does not grow with the number
+            // of rows that hit (the mining sweeps and the start of a retrieval sweep hit in nearly every unit).
             uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(mine + q4 * 4) = make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
             uint32_t pm = 0u;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) pm |= (w[c] > thr) ? (1u << c) : 0u;
+            for (int c = 0; c < 16; ++c)
+              pm |= (MINING ? (w[c] > thr) : (__uint_as_float(w[c]) >= thr_f)) ? (1u << c) : 0u;
             pm &= ~mu;
             unsigned long long* cb = p.cand + out_row * p.cap;
             const uint32_t col0 = static_cast<uint32_t>(j0 + ucol);
             while (pm) {
               const int c = __ffs(pm) - 1;
               pm &= pm - 1;
-              cb[cnt++] = (static_cast<unsigned long long>(mine[c]) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+              const uint32_t x = mine[c];
+              const uint32_t key = MINING ? x : max(order_key(__uint_as_float(x)), 1u);
+              cb[cnt++] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
             }
             __syncwarp();
-          } else if (hm) {
-            uint32_t* stg = sStage + (warp * 32) * TOPK_STAGE_STRIDE;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(stg + lane * TOPK_STAGE_STRIDE + q4 * 4) =
-                  make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
-            __syncwarp();
-            const int half = lane >> 4, hl = lane & 15;
-            const uint32_t col = static_cast<uint32_t>(j0 + ucol + hl);
-            while (hm) {
-              const int srcA = __ffs(hm) - 1;
-              hm &= hm - 1;
-              int srcB = -1;
-              if (hm) {
-                srcB = __ffs(hm) - 1;
-                hm &= hm - 1;
+            // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
+            // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
+            // column wins ties).
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
+              const int n = __shfl_sync(0xffffffffu, cnt, src);
+              __syncwarp();
+              const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane);
+              __syncwarp();
+              if (lane == src) {
+                cnt = p.keep;
+                const uint32_t kk = static_cast<uint32_t>(kth >> 32);
+                thr = kk > 0 ? kk - 1 : 0;
+                thr_f = order_key_inv(kk);
               }
-              const bool act = half == 0 || srcB >= 0;
-              const int src = (half != 0 && srcB >= 0) ? srcB : srcA;
-              const uint32_t x = stg[src * TOPK_STAGE_STRIDE + hl];
-              const uint32_t m_src = __shfl_sync(0xffffffffu, mu, src);
-              const int cnt_src = __shfl_sync(0xffffffffu, cnt, src);
-              bool pass;
-              uint32_t key;
-              if (!MINING) {
-                const float t_src = __shfl_sync(0xffffffffu, thr_f, src);
-                const float S = __uint_as_float(x);
-                pass = S >= t_src;
-                key = max(order_key(S), 1u);
-              } else {
-                const uint32_t t_src = __shfl_sync(0xffffffffu, thr, src);
-                pass = x > t_src;
-                key = x;
-              }
-              pass = pass && act && !((m_src >> hl) & 1u);
-              const uint32_t pm = __ballot_sync(0xffffffffu, pass);
-              const uint32_t pmh = half ? (pm >> 16) : (pm & 0xffffu);
-              if (pass) {
-                unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
-                buf[cnt_src + __popc(pmh & ((1u << hl) - 1u))] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~col);
-              }
-              if (lane == srcA) cnt += __popc(pm & 0xffffu);
-              if (lane == srcB) cnt += __popc(pm >> 16);
-            }
-            __syncwarp();
-          }
-          // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
-          // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
-          // column wins ties).
-          uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
-            const int n = __shfl_sync(0xffffffffu, cnt, src);
-            __syncwarp();
-            const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane);
-            __syncwarp();
-            if (lane == src) {
-              cnt = p.keep;
-              const uint32_t kk = static_cast<uint32_t>(kth >> 32);
-              thr = kk > 0 ? kk - 1 : 0;
-              thr_f = order_key_inv(kk);
             }
           }
         }
