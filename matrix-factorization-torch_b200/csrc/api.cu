@@ -276,7 +276,7 @@ struct LossWs {
   bool mining;
   SweepPlan fwd, fq, gq, gi;   // forward / mining sweep, merged forward + dQ sweep, dQ sweep, dI sweep
   size_t qprep, iprep, qaug, iaug, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
-      ueff, flag, qg, qs, qaugb, csign, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
+      ueff, flag, qg, qs, qaugb, csign, kvec, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
 
 static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
@@ -328,6 +328,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->qs = take(rowb * B);
   w->qaugb = take(static_cast<size_t>(AUG_COLS) * 2 * B);
   w->csign = take(sizeof(uint32_t) * (cdiv(B, 32) + 4));
+  w->kvec = take(sizeof(float) * (w->B_pad + 4));   // |k_j| per query (+ the upstream sign behind it)
   const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
   w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
   w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * MAX_EPI_PARTS * w->B_pad);
@@ -468,7 +469,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       const CUtensorMap* tmQc = &tmQ;
       const CUtensorMap* tmQca = &tmQa;
       CUtensorMap tmQs, tmQab;
-      if (grad_expfast(lm)) {
+      if (lm_single(lm)) {
         // exponential loss: fold sign, offset and magnitude of every query into the streamed operand and its aug
         // block, so the epilogue of the item-major sweep needs no per-column parameters
         float cabs = fabsf(desc->sigma) * 1.4426950408889634f;
@@ -476,17 +477,22 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
         uint32_t* csign = reinterpret_cast<uint32_t*>(ws + w.csign);
         if (cudaMemsetAsync(csign, 0, sizeof(uint32_t) * (cdiv(B, 32) + 4), st) != cudaSuccess)
           return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
+        float* kvec = reinterpret_cast<float*>(ws + w.kvec);
+        if (cudaMemsetAsync(kvec, 0, sizeof(float) * (w.B_pad + 4), st) != cudaSuccess)
+          return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
         grad_fold_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
-            B, w.kp, w.parts, qprep, reinterpret_cast<const float*>(ws + w.qn2), qg, cabs,
-            reinterpret_cast<__nv_bfloat16*>(ws + w.qs), reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), csign);
+            B, w.kp, w.parts, lm, qprep, reinterpret_cast<const float*>(ws + w.qn2), qg, cabs, ueff,
+            reinterpret_cast<__nv_bfloat16*>(ws + w.qs), reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), csign, kvec,
+            kvec + w.B_pad);
         XB_LAUNCHED();
         if ((rc = make_operand_map(&tmQs, ws + w.qs, B, static_cast<long long>(w.parts) * w.kp))) return rc;
         if ((rc = make_aug_map(&tmQab, ws + w.qaugb, B))) return rc;
         tmQc = &tmQs;
         tmQca = &tmQab;
         p.cabs = cabs;
-        p.gsign_src = ueff + (lm == LM_INFONCE ? XB_LOSS_INFONCE : XB_LOSS_MINE);
+        p.gsign_src = kvec + w.B_pad;
         p.csign = csign;
+        p.kvec = kvec;
       }
       if (w.gi.nchunks == 1) {
         // one column chunk: item rows beyond the in-batch block get their gradient straight from the sweep

@@ -422,13 +422,25 @@ __global__ void grad_params_kernel(int B, int lm, const float* __restrict__ u, f
 // The second MMA multiplies |G| by the same sign-folded tile, so sign(k_j) = s'_j sign(u) is applied by the operand and
 // a global sign(u) on the way out.  Queries without a gradient (k = 0, target 0, empty rows) fold to all-zero
 // operands and o = -300 / c, i.e. |G| = 0.  csign bit j = [s'_j < 0] (needed for the row sums of G only).
-__global__ void grad_fold_kernel(int B, int kp, int parts, const __nv_bfloat16* __restrict__ qprep,
+__global__ void grad_fold_kernel(int B, int kp, int parts, int lm, const __nv_bfloat16* __restrict__ qprep,
                                  const float* __restrict__ qn2, const float* __restrict__ qg, float cabs,
-                                 __nv_bfloat16* __restrict__ qs, __nv_bfloat16* __restrict__ qaug,
-                                 uint32_t* __restrict__ csign) {
+                                 const float* __restrict__ u, __nv_bfloat16* __restrict__ qs,
+                                 __nv_bfloat16* __restrict__ qaug, uint32_t* __restrict__ csign,
+                                 float* __restrict__ kvec, float* __restrict__ gsign) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // sign of the upstream gradient the per-query factors k_j carry (k_j = sigma s_j u w_j [/ cnt_j])
+    float uu = 0.f;
+    if (lm == LM_CONTR) uu = u[1] + u[2];
+    if (lm == LM_INFONCE) uu = u[3];
+    if (lm == LM_MINE) uu = u[4];
+    if (lm == LM_HINGE) uu = u[5];
+    if (lm == LM_LOGI) uu = u[6];
+    *gsign = uu < 0.f ? -1.f : 1.f;
+  }
   if (row >= B) return;
+  const bool expo = grad_expfast(lm);
   const float4 g = reinterpret_cast<const float4*>(qg)[row];   // {a2, off, k, 0}
   const bool live = g.z != 0.f && fabsf(g.z) <= 3.0e38f && fabsf(g.y) <= 3.0e38f && g.x != 0.f;
   const float sg = !live ? 0.f : (g.x > 0.f ? 1.f : -1.f);
@@ -442,7 +454,8 @@ __global__ void grad_fold_kernel(int B, int kp, int parts, const __nv_bfloat16* 
     else { x.x ^= flip; x.y ^= flip; x.z ^= flip; x.w ^= flip; }
     dst[k] = x;
   }
-  const float o = live ? (g.y + log2f(fabsf(g.z))) / cabs : -300.f / cabs;
+  // exponential losses fold the magnitude into the offset (|G| = 2^x); the others keep |k_j| per column (kvec)
+  const float o = live ? (g.y + (expo ? log2f(fabsf(g.z)) : 0.f)) / cabs : -300.f / cabs;
   const float t = sg * (-0.5f * qn2[row]) + o;
   const __nv_bfloat16 t0 = __float2bfloat16_rn(t);
   const float r1 = t - __bfloat162float(t0);
@@ -453,7 +466,10 @@ __global__ void grad_fold_kernel(int B, int kp, int parts, const __nv_bfloat16* 
   __nv_bfloat16 v = zero;
   if (lane >= 16) v = k == 0 ? t0 : (k == 1 ? t1 : (k == 2 ? t2 : (k < 6 ? sb : zero)));
   qaug[static_cast<size_t>(row) * 32 + lane] = v;
-  if (lane == 0 && sg < 0.f) atomicOr(csign + (row >> 5), 1u << (row & 31));
+  if (lane == 0) {
+    kvec[row] = live ? fabsf(g.z) : 0.f;
+    if (sg < 0.f) atomicOr(csign + (row >> 5), 1u << (row & 31));
+  }
 }
 
 template <typename T>

@@ -122,6 +122,7 @@ struct SweepParams {
   float cabs;                // |sigma| * log2(e)
   const float* gsign_src;    // upstream gradient scalar; its sign multiplies the accumulator on the way out
   const uint32_t* csign;     // bit j set <=> column (query) j enters with a negative sign (row sums of G only)
+  const float* kvec;         // item-major sweep of the step / logistic losses: |k_j| per column (query), padded to BN
   const int* cond;           // optional: the launch is a no-op unless *cond != 0 (device-side fallback switch)
   // GRAD, item-major sweep with a single column chunk: row blocks at or beyond final_row0 (no in-batch diagonal terms
   // there) write dI = acc - colsum(G) * v straight from the accumulator instead of the fp32 partials
@@ -272,11 +273,42 @@ __device__ __forceinline__ void fwd_unit(const uint32_t (&s)[16], uint32_t m16, 
   }
 }
 
+// Item-major gradient unit of the step / logistic losses with folded operands (grad_fold_kernel): x = xa * T + xo with
+// T = s'_j S_ij + off_j / c straight from the tensor core; |G_ij| = |k_j| phi(x), phi = [x > 0] (contrastive, hinge) or
+// 1 / (1 + 2^-x) (logistic); |k_j| comes from global memory with a warp-uniform address (one L1 line per unit).
+template <int LM, bool MASKED, bool SIGNED>
+__device__ __forceinline__ void grad_foldk_unit(const uint32_t (&s)[16], uint32_t m16, uint32_t sg16, float xa, float xo,
+                                                const float* __restrict__ kcol, float2& rs, float2& rn,
+                                                uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    const float2 x = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), make_float2(xa, xa),
+                           make_float2(xo, xo));
+    const float2 kv = __ldg(reinterpret_cast<const float2*>(kcol + c));
+    float e0, e1;
+    if (LM & LM_LOGI) {
+      e0 = kv.x * rcpf(1.f + ex2f(-x.x));
+      e1 = kv.y * rcpf(1.f + ex2f(-x.y));
+    } else {
+      e0 = x.x > 0.f ? kv.x : 0.f;
+      e1 = x.y > 0.f ? kv.y : 0.f;
+    }
+    if (MASKED) {
+      e0 = ((m16 >> c) & 1u) ? 0.f : e0;
+      e1 = ((m16 >> (c + 1)) & 1u) ? 0.f : e1;
+    }
+    rs = fadd2(rs, make_float2(e0, e1));
+    if (SIGNED) rn = fadd2(rn, make_float2(((sg16 >> c) & 1u) ? e0 : 0.f, ((sg16 >> (c + 1)) & 1u) ? e1 : 0.f));
+    pk[c >> 1] = pack_bf16x2(e0, e1);
+  }
+}
+
 // Lean gradient unit of the exponential losses: |G| = 2^(xa * S + xo [- lq2_col]), masked columns -> 0, row sum in
 // `rs` (packed pair), bf16 pairs in pk.  `lqp` (LogQ, query-major sweep only) = float2 per column {-, lq2} in smem.
-template <bool LOGQ_COL, bool MASKED>
+template <bool LOGQ_COL, bool MASKED, bool SIGNED = false>
 __device__ __forceinline__ void grad_fast_unit(const uint32_t (&s)[16], uint32_t m16, float xa, float xo,
-                                               const float2* __restrict__ lqp, float2& rs, uint32_t (&pk)[8]) {
+                                               const float2* __restrict__ lqp, float2& rs, uint32_t (&pk)[8],
+                                               uint32_t sg16 = 0u, float2* rn = nullptr) {
 #pragma unroll
   for (int c = 0; c < 16; c += 2) {
     float2 x = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), make_float2(xa, xa),
@@ -297,6 +329,7 @@ __device__ __forceinline__ void grad_fast_unit(const uint32_t (&s)[16], uint32_t
       e1 = ((m16 >> (c + 1)) & 1u) ? 0.f : e1;
     }
     rs = fadd2(rs, make_float2(e0, e1));
+    if (SIGNED) *rn = fadd2(*rn, make_float2(((sg16 >> c) & 1u) ? e0 : 0.f, ((sg16 >> (c + 1)) & 1u) ? e1 : 0.f));
     pk[c >> 1] = pack_bf16x2(e0, e1);
   }
 }
@@ -501,6 +534,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   constexpr bool EXPFAST = (MODE == MODE_GRAD || FWDQ) && grad_expfast(LM);
   static_assert(!FWDQ || (EXPFAST && QROW), "MODE_FWDQ exists for the query-major sweep of the exponential losses only");
   constexpr bool FOLDED = EXPFAST && !QROW;              // column operand = sign-folded queries (grad_fold_kernel)
+  // ... the same folding for the other single-loss gradients of the item-major sweep; only |k_j| stays per column
+  constexpr bool FOLDK = (MODE == MODE_GRAD) && !QROW && LM != 0 && lm_single(LM) && !grad_expfast(LM);
+  constexpr bool FOLD_ANY = FOLDED || FOLDK;
   // score-tile buffers in TMEM: without a gradient accumulator all 512 columns hold S tiles, so the MMA thread can
   // run three tiles ahead of the epilogue and the per-tile barrier hand-shakes leave the critical path
   const int NSB = HAS_G ? grad_bufs(p.kp) : 4;
@@ -780,6 +816,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         xo = LOGQ ? -rp_reg[1] : 0.f;
         oscale = (p.gsign_src != nullptr && *p.gsign_src < 0.f) ? -1.f : 1.f;
       }
+    } else if (FOLDK) {
+      xa = p.cabs;
+      xo = LOGQ ? -rp_reg[1] : 0.f;
+      oscale = (p.gsign_src != nullptr && *p.gsign_src < 0.f) ? -1.f : 1.f;
     }
 
     const uint32_t* mrow = (p.mask != nullptr) ? p.mask + static_cast<size_t>(row) * p.mask_words : nullptr;
@@ -801,7 +841,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // staged column parameters: the item side only carries the LogQ term (the norms ride in the contraction); the
     // query-side gradient blocks of the item-major sweep are staged unless the lean path folded them away
     constexpr bool use_cpar =
-        ((MODE == MODE_FWD || FWDQ) && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLDED)));
+        ((MODE == MODE_FWD || FWDQ) && LOGQ) || (MODE == MODE_GRAD && ((QROW && LOGQ) || (!QROW && !FOLD_ANY)));
     constexpr bool ALWAYS_MASK = (MODE == MODE_FWD || MODE == MODE_GRAD || FWDQ);   // the loss sweeps always carry one
     auto fetch_mask = [&](int tile, uint32_t& m0, uint32_t& m1) {
       const int jt = tile * BN;
@@ -831,7 +871,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     auto fetch_sign = [&](int tile, uint32_t& s0, uint32_t& s1) {
       s0 = 0u;
       s1 = 0u;
-      if (FOLDED) {
+      if (FOLD_ANY) {
         const int w = (tile * BN + PW * part) >> 5;
         s0 = __ldg(p.csign + w);
         if (PW == 64) s1 = __ldg(p.csign + w + 1);
@@ -937,21 +977,32 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           uint32_t pk[8];
           const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
           float2 us = make_float2(0.f, 0.f);
-          if (__any_sync(0xffffffffu, mu != 0u)) grad_fast_unit<QROW && LOGQ, true>(s, mu, xa, xo, lqp, us, pk);
-          else grad_fast_unit<QROW && LOGQ, false>(s, mu, xa, xo, lqp, us, pk);
-          rs2 = fadd2(rs2, us);
-          if (FOLDED) {
-            // row sums need the column signs; a unit with negative-sign columns (signed targets) re-adds those
-            const uint32_t sgw = (k * UW < 32) ? sg0 : sg1;
-            const uint32_t su = (sgw >> ((k * UW) & 31)) & 0xffffu;
-            if (su != 0u) {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const uint32_t h = (c & 1) ? (pk[c >> 1] & 0xffff0000u) : (pk[c >> 1] << 16);
-                if ((su >> c) & 1u) rneg += __uint_as_float(h);
-              }
-            }
+          // row sums need the column signs: a unit with negative-sign columns (signed targets) also sums those apart
+          const uint32_t sgw = (k * UW < 32) ? sg0 : sg1;
+          const uint32_t su = FOLDED ? ((sgw >> ((k * UW) & 31)) & 0xffffu) : 0u;
+          if (FOLDED && su != 0u) {
+            float2 un = make_float2(0.f, 0.f);
+            grad_fast_unit<QROW && LOGQ, true, true>(s, mu, xa, xo, lqp, us, pk, su, &un);
+            rneg += un.x + un.y;
+          } else if (__any_sync(0xffffffffu, mu != 0u)) {
+            grad_fast_unit<QROW && LOGQ, true>(s, mu, xa, xo, lqp, us, pk);
+          } else {
+            grad_fast_unit<QROW && LOGQ, false>(s, mu, xa, xo, lqp, us, pk);
           }
+          rs2 = fadd2(rs2, us);
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
+        } else if constexpr (FOLDK) {
+          uint32_t pk[8];
+          float2 us = make_float2(0.f, 0.f);
+          const float* kcol = p.kvec + j0 + ucol;
+          const uint32_t sgw = (k * UW < 32) ? sg0 : sg1;
+          const uint32_t su = (sgw >> ((k * UW) & 31)) & 0xffffu;
+          float2 un = make_float2(0.f, 0.f);
+          if (su != 0u) grad_foldk_unit<LM, true, true>(s, mu, su, xa, xo, kcol, us, un, pk);
+          else if (__any_sync(0xffffffffu, mu != 0u)) grad_foldk_unit<LM, true, false>(s, mu, 0u, xa, xo, kcol, us, un, pk);
+          else grad_foldk_unit<LM, false, false>(s, mu, 0u, xa, xo, kcol, us, un, pk);
+          rs2 = fadd2(rs2, us);
+          rneg += un.x + un.y;
           tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (MODE == MODE_GRAD) {
           uint32_t pk[8];
@@ -1138,7 +1189,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     bool direct = false;
     if constexpr (MODE == MODE_GRAD && !QROW) direct = p.out_final != nullptr && rb * BM >= p.final_row0;
     if (HAS_G && direct) {
-      if (EXPFAST) rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
+      if (EXPFAST || FOLDK) rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
       // column sum of G for this row = sum over the column parts (one thread each): exchange through shared memory
       float* sref = sPar;
       named_bar_sync(3, EPI_THREADS);                 // every warp is done with the staged column parameters
@@ -1171,7 +1222,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float x = __uint_as_float(a[c + u]) * (EXPFAST ? oscale : 1.f);
+            const float x = __uint_as_float(a[c + u]) * ((EXPFAST || FOLDK) ? oscale : 1.f);
             o32[c + u] = x - cg * vv[u];
           }
         }
@@ -1210,11 +1261,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         for (int c = 0; c < 32; c += 4) {
           float4 x = make_float4(__uint_as_float(a[c]), __uint_as_float(a[c + 1]), __uint_as_float(a[c + 2]),
                                  __uint_as_float(a[c + 3]));
-          if (EXPFAST) { x.x *= oscale; x.y *= oscale; x.z *= oscale; x.w *= oscale; }
+          if (EXPFAST || FOLDK) { x.x *= oscale; x.y *= oscale; x.z *= oscale; x.w *= oscale; }
           *reinterpret_cast<float4*>(o + cc * 32 + c) = x;
         }
       }
-      if (EXPFAST) {
+      if (EXPFAST || FOLDK) {
         rg = ((rs2.x + rs2.y) - 2.f * rneg) * oscale;
         rgh = 0.f;
       }
