@@ -173,14 +173,15 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
 
 static inline int mask_words_for(int ncols) { return 4 * cdiv(ncols, BN); }
 
-// Single-loss calls of the exponential losses run the forward statistics and the query-side gradient in ONE sweep
-// (MODE_FWDQ); the two separate sweeps stay behind as a device-side fallback.  XB_MERGE_FWDQ=0 turns the merge off.
+// Single-loss calls run the forward statistics and the query-side gradient in ONE sweep (MODE_FWDQ).  For the
+// exponential losses the two separate sweeps stay behind as a device-side fallback (their per-row exponent reference
+// can overflow); the step / logistic losses have nothing to normalise and need none.  XB_MERGE_FWDQ=0 turns it off.
 static bool merged_fwdq(int lm, bool mining) {
   static const bool enabled = [] {
     const char* e = std::getenv("XB_MERGE_FWDQ");
     return e == nullptr || e[0] != '0';
   }();
-  return enabled && !mining && grad_expfast(lm);
+  return enabled && !mining && lm != 0 && lm_single(lm);
 }
 
 static inline int sweep_lm_from_mask(uint32_t loss_mask) {
@@ -442,7 +443,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     fq_part = merged ? reinterpret_cast<const float*>(ws + w.part) : nullptr;
     fq_qg = qg;
     fq_flag = flag;
-    {  // dQ sweep: rows = queries, columns = items (with the merged forward: only as its fallback)
+    if (!merged || grad_expfast(lm)) {  // dQ sweep: rows = queries, columns = items (merged forward: only as its fallback)
       SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
       p.use_aug = 1;
       p.cond = merged ? flag : nullptr;
@@ -454,9 +455,9 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       p.out_stats = rsq;
       XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
                                      w.gq.smem, st));
-      nq = w.gq.nchunks;
-      nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
     }
+    nq = w.gq.nchunks;
+    nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
     {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
       p.use_aug = 1;
@@ -519,7 +520,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   }
   grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
       B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
-      dq, gdiag, fq_part, fq_qg, fq_flag);
+      dq, gdiag, fq_part, fq_qg, fq_flag, lm);
   XB_LAUNCHED();
   grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(n_final_rows) * 32, 256), 256, 0, st>>>(
       n_final_rows, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
@@ -680,16 +681,19 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                    w.fq.smem, st));
         loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fq.nchunks * epi_parts(MODE_FWDQ, lm, true), p.out_stats, desc->sigma,
                                                        reinterpret_cast<float4*>(ws + w.rowinfo),
-                                                       reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, flag, nullptr);
+                                                       reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss,
+                                                       grad_expfast(lm) ? flag : nullptr, nullptr);
         XB_LAUNCHED();
         p.cond = flag;
       }
-      XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
-      loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
-                                                     reinterpret_cast<float4*>(ws + w.rowinfo),
-                                                     reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr,
-                                                     merged ? flag : nullptr);
-      XB_LAUNCHED();
+      if (!merged || grad_expfast(lm)) {   // the plain forward sweep: the only path, or the exponential losses' fallback
+        XB_SWEEP(launch_sweep_fwd(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
+        loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_FWD, lm, true), p.out_stats, desc->sigma,
+                                                       reinterpret_cast<float4*>(ws + w.rowinfo),
+                                                       reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr,
+                                                       merged ? flag : nullptr);
+        XB_LAUNCHED();
+      }
     } else {
       // semi-hard mining (losses.py:134-162): streaming selection of the K best columns per row, then
       // the sparse loss on those columns

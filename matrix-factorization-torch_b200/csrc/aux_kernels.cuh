@@ -510,13 +510,14 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
                                        const float4* __restrict__ rowinfo, const float4* __restrict__ rowstat,
                                        T* __restrict__ dq, float* __restrict__ gdiag,
                                        const float* __restrict__ fq_part, const float* __restrict__ fq_qg,
-                                       const int* __restrict__ fq_flag) {
+                                       const int* __restrict__ fq_flag, int lm) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
-  // Merged forward + dQ sweep (MODE_FWDQ, fq_part != nullptr and no fallback): chunk c holds acc_c = sum_j 2^(x_ij -
-  // m_ic) v_j and its column parts se_icp = sum_j 2^(x_ij - m_ic); with G_ij = k_i 2^(x_ij + off_i) both scale by
-  // f_ic = k_i 2^(m_ic + off_i).  Otherwise acc / rs_part come from the dQ sweep and f = 1.
+  // Merged forward + dQ sweep (MODE_FWDQ, fq_part != nullptr and no fallback).  Exponential losses: chunk c holds
+  // acc_c = sum_j 2^(x_ij - m_ic) v_j and its column parts se_icp = sum_j 2^(x_ij - m_ic); with G_ij = k_i 2^(x_ij +
+  // off_i) both scale by f_ic = k_i 2^(m_ic + off_i).  Step / logistic losses: acc_c = sum_j G'_ij v_j, se = sum_j G'_ij
+  // and f = k_i.  Otherwise acc / rs_part come from the dQ sweep and f = 1.
   const bool scaled = fq_part != nullptr && *fq_flag == 0;
   const int ep = nchunks > 0 ? nsub / nchunks : 1;
   float fk = 0.f, foff = 0.f;
@@ -526,8 +527,10 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
     fk = live ? g.z : 0.f;
     foff = live ? g.y : 0.f;
   }
+  const bool expo = grad_expfast(lm);
   auto factor_of = [&](int c) {   // 0 for a dead row: its accumulator may hold inf / NaN from an overflowed reference
     if (!scaled) return 1.f;
+    if (!expo) return fk;
     return fk != 0.f ? fk * exp2f(fq_part[(static_cast<size_t>(c) * ep * nR_pad + row) * 8 + 4] + foff) : 0.f;
   };
   // the usual case (<= 32 column chunks): lane c keeps chunk c's factor, the loops below fetch it with a shuffle
@@ -544,6 +547,7 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rg += __shfl_xor_sync(0xffffffffu, rg, o);
+    if (lm & (LM_HINGE | LM_LOGI)) rgh = rg;   // the pairwise losses' share of the row sum feeds dL/dL_ii
   } else {
     for (int c = 0; c < nsub; ++c) {
       const float2 r = *reinterpret_cast<const float2*>(rs_part + (static_cast<size_t>(c) * nR_pad + row) * 2);

@@ -273,6 +273,50 @@ __device__ __forceinline__ void fwd_unit(const uint32_t (&s)[16], uint32_t m16, 
   }
 }
 
+// Merged forward + dQ unit of the step / logistic losses (MODE_FWDQ): x = a2 * S + xo [- lq2_col];
+//   contrastive / hinge: statistic += relu(x),        G' = [x > 0]
+//   logistic:            statistic += log2(1 + 2^x),  G' = 2^x / (1 + 2^x)
+// G' is the gradient up to the per-row factor k_i, which grad_finalize_q_kernel applies (no reference, no fallback).
+template <int LM, bool LOGQ_COL, bool MASKED>
+__device__ __forceinline__ void fwdq_step_unit(const uint32_t (&s)[16], uint32_t m16, float xa, float xo,
+                                               const float2* __restrict__ lqp, float& stat, float2& rs,
+                                               uint32_t (&pk)[8]) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    float2 x = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), make_float2(xa, xa),
+                     make_float2(xo, xo));
+    if (LOGQ_COL) {
+      const float4 cp = *reinterpret_cast<const float4*>(lqp + c);
+      x.x -= cp.y;
+      x.y -= cp.w;
+    }
+    float v0, v1, e0, e1;
+    if (LM & LM_LOGI) {
+      // softplus and sigmoid from one exponential; beyond x = 40 they are x and 1 to fp32 precision
+      const float t0 = ex2f(fminf(x.x, 40.f)), t1 = ex2f(fminf(x.y, 40.f));
+      v0 = x.x > 40.f ? x.x : lg2f(1.f + t0);
+      v1 = x.y > 40.f ? x.y : lg2f(1.f + t1);
+      e0 = t0 * rcpf(1.f + t0);
+      e1 = t1 * rcpf(1.f + t1);
+    } else {
+      v0 = fmaxf(x.x, 0.f);
+      v1 = fmaxf(x.y, 0.f);
+      e0 = x.x > 0.f ? 1.f : 0.f;
+      e1 = x.y > 0.f ? 1.f : 0.f;
+    }
+    if (MASKED) {
+      const bool k0 = (m16 >> c) & 1u, k1 = (m16 >> (c + 1)) & 1u;
+      v0 = k0 ? 0.f : v0; e0 = k0 ? 0.f : e0;
+      v1 = k1 ? 0.f : v1; e1 = k1 ? 0.f : e1;
+    }
+    acc = fadd2(acc, make_float2(v0, v1));
+    rs = fadd2(rs, make_float2(e0, e1));
+    pk[c >> 1] = pack_bf16x2(e0, e1);
+  }
+  stat += acc.x + acc.y;
+}
+
 // Item-major gradient unit of the step / logistic losses with folded operands (grad_fold_kernel): x = xa * T + xo with
 // T = s'_j S_ij + off_j / c straight from the tensor core; |G_ij| = |k_j| phi(x), phi = [x > 0] (contrastive, hinge) or
 // 1 / (1 + 2^-x) (logistic); |k_j| comes from global memory with a warp-uniform address (one L1 line per unit).
@@ -532,7 +576,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   constexpr int EPI_WARPS = 4 * EP;
   constexpr int EPI_THREADS = 128 * EP;
   constexpr bool EXPFAST = (MODE == MODE_GRAD || FWDQ) && grad_expfast(LM);
-  static_assert(!FWDQ || (EXPFAST && QROW), "MODE_FWDQ exists for the query-major sweep of the exponential losses only");
+  static_assert(!FWDQ || (QROW && LM != 0 && lm_single(LM)), "MODE_FWDQ: query-major sweep of a single loss");
+  constexpr bool FWDQ_EXP = FWDQ && EXPFAST;             // exponential losses: per-row reference, look-ahead tile
+  constexpr bool FWDQ_STEP = FWDQ && !EXPFAST;           // step / logistic losses: nothing to normalise
   constexpr bool FOLDED = EXPFAST && !QROW;              // column operand = sign-folded queries (grad_fold_kernel)
   // ... the same folding for the other single-loss gradients of the item-major sweep; only |k_j| stays per column
   constexpr bool FOLDK = (MODE == MODE_GRAD) && !QROW && LM != 0 && lm_single(LM) && !grad_expfast(LM);
@@ -580,8 +626,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const int t_end = min(t_begin + p.tiles_per_cta, p.n_ctiles);
   const int T0 = t_end - t_begin;                 // column tiles of this CTA
   // FWDQ visits its first tile twice: once to fix the row references (G = 0), then for real
-  const int T = (FWDQ && T0 > 0) ? T0 + 1 : T0;
-  auto tile_of = [&](int t) { return t_begin + (FWDQ ? max(t - 1, 0) : t); };
+  const int T = (FWDQ_EXP && T0 > 0) ? T0 + 1 : T0;
+  auto tile_of = [&](int t) { return t_begin + (FWDQ_EXP ? max(t - 1, 0) : t); };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->r_full, 1);
@@ -801,9 +847,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
 
     // lean exponential-gradient path: x = xa * S + xo, result scaled by oscale on the way out
     float xa = 0.f, xo = -300.f, oscale = 1.f;
-    if (FWDQ) {
+    if (FWDQ_EXP) {
       xa = rp_reg[0];      // a2; the offset -m_i follows from the look-ahead pass
       xo = 0.f;
+    } else if (FWDQ_STEP) {
+      xa = rp_reg[0];      // a2; offsets as in the forward statistics: s m (contrastive) or m - L_ii (pairwise)
+      xo = (LM & LM_CONTR) ? rp_reg[3] : rp_reg[2];
     } else if (EXPFAST) {
       if (QROW) {
         const float k = rp_reg[2];
@@ -898,7 +947,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       const int nb = (b + 1 == NSB) ? 0 : b + 1;                  // next tile's buffer and phase parity
       const uint32_t nph = (b + 1 == NSB) ? (eb.ph ^ 1u) : eb.ph;
       const int j0 = tile_of(t) * BN;
-      const bool look = FWDQ && t == 0;             // look-ahead pass: row maxima only, G = 0
+      const bool look = FWDQ_EXP && t == 0;         // look-ahead pass: row maxima only, G = 0
       const uint32_t buf_addr = tmem_base + lane_off + static_cast<uint32_t>(b * BN) + part_col;
       // column parameters for this tile -> shared (single buffer: barrier before the writes of the next tile)
       float* cpar_s = sPar;
@@ -953,6 +1002,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           const float2* colp = reinterpret_cast<const float2*>(cpar_s) + ucol;
           if (__any_sync(0xffffffffu, mu != 0u)) fwd_unit<LM, LOGQ, true>(s, mu, qp, colp, st);
           else fwd_unit<LM, LOGQ, false>(s, mu, qp, colp, st);
+        } else if constexpr (FWDQ_STEP) {
+          uint32_t pk[8];
+          const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
+          float2 us = make_float2(0.f, 0.f);
+          if (__any_sync(0xffffffffu, mu != 0u)) fwdq_step_unit<LM, LOGQ, true>(s, mu, xa, xo, lqp, st.csum, us, pk);
+          else fwdq_step_unit<LM, LOGQ, false>(s, mu, xa, xo, lqp, st.csum, us, pk);
+          rs2 = fadd2(rs2, us);
+          tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (FWDQ) {
           uint32_t pk[8];
           const float2* lqp = reinterpret_cast<const float2*>(cpar_s) + ucol;
@@ -1183,8 +1240,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     if (FWDQ) {
       // same layout as the forward statistics: (reference, sum of 2^(x - reference)) of this thread's columns
       float4* o = reinterpret_cast<float4*>(p.out_stats + out_row * 8);
-      o[0] = make_float4(static_cast<float>(ucnt), 0.f, 0.f, 0.f);
-      o[1] = make_float4(mrun, rs2.x + rs2.y, 0.f, 0.f);
+      // (step / logistic losses: the loss statistic sits in its forward slot, the row sum of G' in the `se` slot)
+      const float stat = FWDQ_STEP ? st.csum : 0.f;
+      o[0] = make_float4(static_cast<float>(ucnt), (LM & LM_CONTR) ? stat : 0.f, (LM & LM_HINGE) ? stat : 0.f,
+                         (LM & LM_LOGI) ? stat : 0.f);
+      o[1] = make_float4(FWDQ_STEP ? 0.f : mrun, rs2.x + rs2.y, 0.f, 0.f);
     }
     bool direct = false;
     if constexpr (MODE == MODE_GRAD && !QROW) direct = p.out_final != nullptr && rb * BM >= p.final_row0;

@@ -23,8 +23,11 @@ cudaError_t launch_sweep_fwd(int lm, bool logq, const CUtensorMap& tmR, const CU
 cudaError_t launch_sweep_fwdq(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                               const SweepParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   switch (lm) {
+    XB_FWDQ_CASE(LM_CONTR)
     XB_FWDQ_CASE(LM_INFONCE)
     XB_FWDQ_CASE(LM_MINE)
+    XB_FWDQ_CASE(LM_HINGE)
+    XB_FWDQ_CASE(LM_LOGI)
     default: return cudaErrorInvalidValue;
   }
 }
