@@ -13,21 +13,23 @@
 //   MODE_GRAD  epilogue = G_ij = dLoss/dS_ij as a bf16 tile written back into TMEM (over the score tile it came
 //              from), followed by a second tcgen05.mma  acc[128 x d] += G[128 x 128] . C_tile[128 x d]
 //              (flash-style recompute).  With (R,C) = (Q,I) acc is dQ; with (R,C) = (I,Q) the same kernel yields dI.
-//   MODE_FWDQ  forward statistics AND the query-side gradient in one sweep (exponential losses): P_ij = 2^(x_ij - m_i)
-//              against a per-row reference m_i fixed after a look at the first tile, se_i = sum_j P_ij (the LSE
-//              statistic), acc_i += P_ij v_j by the second MMA.  The backward pass only rescales acc (flash-attention
-//              forward, with the normalisation postponed); the separate dQ sweep is kept as the fallback for rows whose
-//              sums leave the fp32 range.
+//   MODE_FWDQ  forward statistics AND the query-side gradient in one sweep (single-loss calls).  Exponential losses:
+//              P_ij = 2^(x_ij - m_i) against a per-row reference m_i fixed after a look at the first tile, se_i =
+//              sum_j P_ij (the LSE statistic), acc_i += P_ij v_j by the second MMA; the backward pass only rescales acc
+//              (flash-attention forward, with the normalisation postponed), and the separate sweeps stay as the
+//              fallback for rows whose sums leave the fp32 range.  Step / logistic losses: sum relu / softplus and the
+//              unscaled G' = [x > 0] / sigmoid(x), scaled by k_i in the backward pass; nothing to fall back from.
 //   MODE_TOPK  epilogue = streaming per-row top-k selection (retrieval, and the semi-hard negative
 //              mining order of losses.py:134-162)
 //   MODE_DEBUG epilogue = G := S (used by tests to validate both MMA paths against a dense matmul)
 //
-// Warp roles: 4*EP epilogue warps, then the TMA producer warp, then the TMEM allocator + MMA issuer warp (the highest
-// warp id has issue priority on its scheduler: the thread that feeds the tensor core must never queue behind math):
+// Warp roles: 4*EP epilogue warps, then the TMA producer warp, then TWO MMA issuer warps (the first also owns the
+// TMEM allocation; the highest warp ids have issue priority on their schedulers: the threads that feed the tensor
+// core must never queue behind math):
 // thread <-> (TMEM lane = tile row, column part).  EP = 4 (16 epilogue warps) for the single-loss forward / gradient
 // variants, EP = 2 where register pressure is high (all-losses variants, top-k).
 //
-// Epilogue pipeline: a thread walks its columns in UNITS of 16 (32 for top-k).  The tcgen05.ld of unit u+1 is issued
+// Epilogue pipeline: a thread walks its columns in UNITS of 16.  The tcgen05.ld of unit u+1 is issued
 // before the math of unit u, so TMEM latency hides behind the MUFU / FMA work; a score buffer is handed back to the
 // MMA warp as soon as its last unit sits in registers.  Barrier arrivals are one elected lane per warp.
 // Per-row outputs are written per "sub-chunk" = EP * column chunk + column part and merged by the finalisers.

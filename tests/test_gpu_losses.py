@@ -110,6 +110,26 @@ def test_against_oracle_fp32(b, n, d, p, k, sigma, margin, signed, normalize) ->
     assert_close(got, ref, label=f"B{b} N{n} d{d} K{k}")
 
 
+@pytest.mark.parametrize(("signed", "dtype"), [(False, torch.float32), (True, torch.float32), (False, torch.bfloat16)])
+def test_many_item_row_blocks_and_column_chunks(signed: bool, dtype: torch.dtype) -> None:
+    """20,000 items = 157 item row blocks (> 148 SMs): the persistent item-major sweep walks several row blocks per
+    CTA; 256 users = 2 query row blocks, so the query-major sweeps split the items into 40 column chunks (> 32: the
+    per-chunk scaling of the merged forward + dQ sweep leaves its one-factor-per-lane path)."""
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    inp = synthetic.make_loss_inputs(256, 20000, 64, 8, n_catalog=9000, seed=5, signed_targets=signed)
+    got = cuda_losses_and_grads(inp, num_negatives=0, sigma=4.0, margin=0.3, dtype=dtype)
+    ref = oracle_losses_and_grads(inp, num_negatives=0, sigma=4.0, margin=0.3, round_bf16=dtype == torch.bfloat16)
+    if dtype == torch.float32:
+        assert_close(got, ref, label=f"N20000 signed={signed}")
+    else:
+        for n, (loss, dq, dv) in got.items():
+            rloss, rdq, rdv = ref[n]
+            assert abs(float(loss) - float(rloss)) <= RTOL * max(abs(float(rloss)), 1e-6), n
+            assert rel_err(dq, rdq) < 5e-3, n  # output rounding to bf16: 2^-9 per element
+            assert rel_err(dv, rdv) < 5e-3, n
+
+
 @pytest.mark.parametrize("sigma", [60.0, 300.0, 1000.0])
 def test_large_sigma_takes_the_fallback_sweeps(sigma: float) -> None:
     """The merged forward + dQ sweep fixes each row's exponent reference after one tile; with logits spread over
