@@ -298,6 +298,64 @@ def bench_retrieval(device: torch.device, world: int, rank: int, num_items_total
             "tensor_frac_of_burst_peak": flops / (ms * 1e-3) / (pk["bf16_tflops"] * 1e12)}
 
 
+def bench_mns(device: torch.device, world: int, rank: int) -> dict:
+    """Config 3: mixed negative sampling with global negatives - per rank 8,192 users, their 8,192 in-batch items and
+    16,384 uniform negatives, d=256 bf16; items and negatives are all-gathered over NCCL (every rank scores its users
+    against 24,576 x world candidates) and the item gradients are reduced back to their owners in the backward pass."""
+    import torch.distributed as dist  # noqa: PLC0415
+
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    b, u, d, p = 8192, 16384, 256, 32
+    inp = synthetic.make_loss_inputs(b, b + u, d, p, n_catalog=200_000, seed=50 + rank)
+    q = inp["user_embed"].to(device, torch.bfloat16)
+    items = inp["item_embed"][:b].to(device, torch.bfloat16)
+    negs = inp["item_embed"][b:].to(device, torch.bfloat16)
+    target, pos_idx = inp["target"].to(device), inp["pos_idx"].to(device)
+    item_idx, neg_idx = inp["item_idx"][:b].to(device), inp["item_idx"][b:].to(device)
+    module = getattr(xfmr_b200, HEADLINE_LOSS)(sigma=SIGMA, margin=MARGIN)
+
+    qq, ii, nn = q.requires_grad_(True), items.requires_grad_(True), negs.requires_grad_(True)
+    idx_cat = torch.cat([item_idx, neg_idx])
+
+    def step() -> tuple:
+        if world > 1:
+            loss = xfmr_b200.distributed.global_negatives_losses(module, qq, ii, nn, target, item_idx=item_idx,
+                                                                 neg_idx=neg_idx, pos_idx=pos_idx)
+        else:
+            loss = module(qq, torch.cat([ii, nn]), target, item_idx=idx_cat, pos_idx=pos_idx)
+        return (loss, *torch.autograd.grad(loss, (qq, ii, nn)))
+
+    launch = "eager (NCCL collectives inside the step)"
+    if world == 1:
+        step = graphed(step)      # one rank: no collective in the step, replay it like the headline
+        launch = "CUDA-graph replay"
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    e1.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    flops = 6.0 * b * (b + u) * world * d   # per rank: its users against the global candidate set
+    pk = peaks()
+    return {"metric": "mns_global_negatives_samples_per_s", "value": world * b / (ms * 1e-3), "unit": "samples/s",
+            "workload": f"C3: per rank {b} users x ({b} in-batch + {u} uniform) x {world} ranks candidates, d={d} bf16, "
+                        f"sampled-softmax fwd+bwd, NCCL all-gather of items/negatives + gradient reduction",
+            "ms_per_step": ms, "launch": launch, "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+            "tensor_frac_of_sustained_peak": flops / (ms * 1e-3) / (pk["bf16_tflops_sustained"] * 1e12)}
+
+
 def bench_gather(device: torch.device) -> dict:
     import xfmr_b200  # noqa: PLC0415
 
@@ -492,6 +550,8 @@ def main() -> None:  # noqa: PLR0915
         per_loss["all_seven_forward_one_call"] = {"ms_per_step": statistics.median(t)}
         line["per_loss"] = per_loss
         del inp, host
+        torch.cuda.empty_cache()
+        line["mns"] = bench_mns(device, world, rank)
         torch.cuda.empty_cache()
         line["retrieval"] = bench_retrieval(device, world, rank, args.retrieval_items, args.retrieval_queries, 100)
         if rank == 0:
