@@ -145,13 +145,33 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
   SweepPlan pl{};
   pl.n_rblocks = cdiv(nR, BM);
   pl.n_ctiles = cdiv(nC, BN);
-  // loss sweeps: ~2 CTAs per SM.  Selection sweeps (top-k, mining): every column chunk of a row is a separate
-  // candidate stream that starts with an open threshold, so take as few chunks as fill the machine once.
-  int want = ((topk_warps > 0 ? 1 : 2) * NUM_SMS) / (pl.n_rblocks > 0 ? pl.n_rblocks : 1);
-  if (want < 1) want = 1;
-  if (want > pl.n_ctiles) want = pl.n_ctiles;
-  if (want < 1) want = 1;
-  int per = cdiv(pl.n_ctiles, want);
+  // Selection sweeps (top-k, mining): every column chunk of a row is a separate candidate stream that starts with an
+  // open threshold, so take as few chunks as fill the machine once.  Loss sweeps: the chunk count that minimises the
+  // makespan  rounds x (tiles per CTA + per-CTA overhead)  with rounds = ceil(CTAs / SMs) - e.g. 9 chunks for the
+  // 32 query row blocks of config 2 (288 CTAs, 2 rounds of 77 tiles), 1 for its 685 item row blocks.
+  int per;
+  if (topk_warps > 0) {
+    int want = NUM_SMS / (pl.n_rblocks > 0 ? pl.n_rblocks : 1);
+    if (want < 1) want = 1;
+    if (want > pl.n_ctiles) want = pl.n_ctiles;
+    if (want < 1) want = 1;
+    per = cdiv(pl.n_ctiles, want);
+  } else {
+    constexpr int CTA_OVERHEAD_TILES = 4;   // set-up, pipeline fill, accumulator write-out, in units of a tile
+    long long best = -1;
+    per = pl.n_ctiles > 0 ? pl.n_ctiles : 1;
+    const int max_chunks = pl.n_ctiles < 4 ? 1 : (pl.n_ctiles / 4 < 64 ? pl.n_ctiles / 4 : 64);
+    for (int c = 1; c <= max_chunks; ++c) {
+      const int tiles = cdiv(pl.n_ctiles, c);
+      const int chunks = cdiv(pl.n_ctiles, tiles);
+      const long long rounds = cdiv(static_cast<long long>(pl.n_rblocks > 0 ? pl.n_rblocks : 1) * chunks, NUM_SMS);
+      const long long span = rounds * (tiles + CTA_OVERHEAD_TILES);
+      if (best < 0 || span < best) {
+        best = span;
+        per = tiles;
+      }
+    }
+  }
   const int min_per = pl.n_ctiles < 4 ? pl.n_ctiles : 4;
   if (per < min_per) per = min_per;
   if (per < 1) per = 1;

@@ -568,27 +568,33 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
   const __nv_bfloat16* v = ip + static_cast<size_t>(row) * parts * kp;
   const float cq = rg + gii;
   if ((d & 3) == 0) {
-    for (int k = lane * 4; k < d; k += 128) {
+    for (int k0 = 0; k0 < d; k0 += 128) {   // (uniform trip count: factor() shuffles across the whole warp)
+      const int k = k0 + lane * 4;
+      const bool mine = k < d;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int c = 0; c < nchunks; ++c) {
-        const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
         const float f = factor(c);
-        if (f != 0.f) {
+        if (mine && f != 0.f) {
+          const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
           s.x = fmaf(f, x.x, s.x); s.y = fmaf(f, x.y, s.y); s.z = fmaf(f, x.z, s.z); s.w = fmaf(f, x.w, s.w);
         }
       }
+      if (!mine) continue;
       const float4 qv = prepped_val4(q, kp, parts, k), vv = prepped_val4(v, kp, parts, k);
       store_out4<T>(dq + static_cast<size_t>(row) * d + k,
                     make_float4(s.x + gii * vv.x - cq * qv.x, s.y + gii * vv.y - cq * qv.y,
                                 s.z + gii * vv.z - cq * qv.z, s.w + gii * vv.w - cq * qv.w));
     }
   } else {
-    for (int k = lane; k < d; k += 32) {
+    for (int k0 = 0; k0 < d; k0 += 32) {
+      const int k = k0 + lane;
+      const bool mine = k < d;
       float s = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         const float f = factor(c);
-        if (f != 0.f) s = fmaf(f, acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k], s);
+        if (mine && f != 0.f) s = fmaf(f, acc[(static_cast<size_t>(c) * nR_pad + row) * kp + k], s);
       }
+      if (!mine) continue;
       const float qv = prepped_val(q, kp, parts, k), vv = prepped_val(v, kp, parts, k);
       store_out<T>(dq + static_cast<size_t>(row) * d + k, s + gii * vv - cq * qv);
     }

@@ -99,6 +99,7 @@ def test_reference_golden_bf16_io(name: str) -> None:
     (300, 2000, 128, 16, 8, 10.0, 0.2, False, True),  # mining across chunks
     (64, 1500, 96, 8, 0, 1.0, 1.0, False, False),     # un-normalised embeddings exercise the norm terms
     (256, 700, 40, 40, 0, 30.0, -1.0, True, True),    # P > N/20, large sigma, negative margin
+    (100, 32768, 32, 4, 0, 2.0, 0.5, False, True),    # one query row block: 64 column chunks (> one factor per lane)
 ])
 def test_against_oracle_fp32(b, n, d, p, k, sigma, margin, signed, normalize) -> None:  # noqa: ANN001, PLR0913
     from xfmr_b200 import synthetic  # noqa: PLC0415
