@@ -219,41 +219,60 @@ __global__ void hash_fill_kernel(int ncols, const int* __restrict__ slot_of, con
   cols[start[slot] + atomicAdd(fill + slot, 1)] = j;
 }
 
-// one thread per (row, list entry); entry index list_len stands for row_ids0[row]
+// one thread per (row, list entry); entry index list_len stands for row_ids0[row].  Short runs are marked by their
+// thread; a long run (a popular id of a Zipf batch sits in hundreds of columns) is marked by the whole warp.
 __global__ void hash_mark_kernel(int nrows, int list_len, const long long* __restrict__ row_ids0,
                                  const long long* __restrict__ row_lists, const long long* __restrict__ keys,
                                  const int* __restrict__ cnt, const int* __restrict__ start,
                                  const int* __restrict__ cols, int tmask, uint32_t* mask, int words, uint32_t* mask_t,
                                  int words_t) {
+  constexpr int LONG_RUN = 48;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int per_row = list_len + 1;
-  if (gid >= static_cast<long long>(nrows) * per_row) return;
-  const int r = static_cast<int>(gid / per_row);
-  const int e = static_cast<int>(gid % per_row);
-  long long id;
-  if (e == list_len) {
-    if (row_ids0 == nullptr) return;
-    id = row_ids0[r];
-  } else {
-    id = row_lists[static_cast<size_t>(r) * list_len + e];
+  int r = 0, n = 0;
+  const int* run = cols;
+  if (gid < static_cast<long long>(nrows) * per_row) {
+    r = static_cast<int>(gid / per_row);
+    const int e = static_cast<int>(gid % per_row);
+    long long id = EMPTY_KEY;
+    if (e == list_len) {
+      if (row_ids0 != nullptr) id = row_ids0[r];
+    } else {
+      id = row_lists[static_cast<size_t>(r) * list_len + e];
+    }
+    if (id != EMPTY_KEY) {
+      uint32_t slot = hash64(id) & tmask;
+      while (true) {
+        const long long k = keys[slot];
+        if (k == EMPTY_KEY) break;
+        if (k == id) {
+          n = cnt[slot];
+          run = cols + start[slot];
+          break;
+        }
+        slot = (slot + 1) & tmask;
+      }
+    }
   }
-  if (id == EMPTY_KEY) return;
-  uint32_t slot = hash64(id) & tmask;
-  while (true) {
-    const long long k = keys[slot];
-    if (k == EMPTY_KEY) return;
-    if (k == id) break;
-    slot = (slot + 1) & tmask;
+  auto mark = [&](int row, int c) {
+    atomicOr(mask + static_cast<size_t>(row) * words + (c >> 5), 1u << (c & 31));
+    if (mask_t != nullptr) atomicOr(mask_t + static_cast<size_t>(c) * words_t + (row >> 5), 1u << (row & 31));
+  };
+  // long runs: one at a time, all 32 lanes
+  uint32_t heavy = __ballot_sync(0xffffffffu, n > LONG_RUN);
+  while (heavy) {
+    const int src = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const int hn = __shfl_sync(0xffffffffu, n, src);
+    const int hr = __shfl_sync(0xffffffffu, r, src);
+    const unsigned long long hp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(run), src);
+    const int* hrun = reinterpret_cast<const int*>(hp);
+    for (int i = lane; i < hn; i += 32) mark(hr, hrun[i]);
   }
-  const int n = cnt[slot];
-  const int* run = cols + start[slot];
-  uint32_t* mrow = mask + static_cast<size_t>(r) * words;
-  const uint32_t rbit = 1u << (r & 31);
+  if (n <= LONG_RUN) {
 #pragma unroll 4
-  for (int i = 0; i < n; ++i) {
-    const int c = run[i];
-    atomicOr(mrow + (c >> 5), 1u << (c & 31));
-    if (mask_t != nullptr) atomicOr(mask_t + static_cast<size_t>(c) * words_t + (r >> 5), rbit);
+    for (int i = 0; i < n; ++i) mark(r, run[i]);
   }
 }
 
