@@ -89,6 +89,30 @@ int xb_loss_backward(const xb_loss_desc* desc, const float* d_losses, void* d_us
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Uniformity (extension; no code in the reference, which only cites DirectAU / MAWU, README.md:22-25):
+ *   loss = log( 1/(n(n-1)) * sum_{i != j} exp(-t * |x_i - x_j|^2) )       (Wang & Isola 2020; DirectAU's
+ * `uniformity`, t = 2).  It is the Gram contraction X.X^T through the same sweep kernel as the losses
+ * (rows = columns = x, only the diagonal masked), reduced over all pairs instead of per row; the
+ * gradient needs one sweep (the pair weights are symmetric, so dX = 2 * the row-side gradient).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct xb_uniformity_desc {
+  int32_t n;         /* rows of x, >= 2                          */
+  int32_t dim;       /* d (<= 256 bf16, <= 128 split)            */
+  int32_t in_dtype;  /* XB_DTYPE_* of x and d_x                  */
+  int32_t compute;   /* XB_COMPUTE_*                             */
+  float t;           /* temperature, > 0 (DirectAU: 2)           */
+  int32_t reserved;
+} xb_uniformity_desc;
+
+size_t xb_uniformity_workspace_bytes(const xb_uniformity_desc* desc);
+/* loss_out[1] (fp32).  The workspace keeps what the backward needs. */
+int xb_uniformity_forward(const xb_uniformity_desc* desc, const void* x, float* loss_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* d_loss[1] (fp32) upstream gradient; writes d_x [n, d] in desc->in_dtype. */
+int xb_uniformity_backward(const xb_uniformity_desc* desc, const float* d_loss, void* d_x, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Exact top-k retrieval.  Replaces the LanceDB query of ItemProcessor.search
  * (xfmr_rec/data/lightning.py:247-258): score = q . i (cosine for unit-norm embeddings), excluded
  * items removed BEFORE ranking, k best by (score desc, item id asc).
@@ -124,6 +148,27 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
 int xb_topk_merge(int32_t num_queries, int32_t num_lists, int32_t list_len, int32_t k,
                   const float* in_scores, const int64_t* in_ids, float* scores_out, int64_t* ids_out,
                   void* stream);
+
+/* Sparse exclusion lists (the `NOT IN (exclude_item_ids)` prefilter of data/lightning.py:247-252 for catalogs too
+ * large for a dense exclusion mask): in_scores / in_ids [Q, list_len] is a ranked list (e.g. xb_topk_search with
+ * k = list_len), excl_ids [Q, excl_len] int64 padded with INT64_MIN.  Writes the first k entries whose id is not
+ * excluded (-inf / -1 when fewer remain).  Equal to filtering BEFORE ranking whenever
+ * list_len >= k + (number of excluded ids of the query), which the caller guarantees with list_len = k + excl_len. */
+int xb_topk_filter(int32_t num_queries, int32_t list_len, int32_t k, int32_t excl_len, const float* in_scores,
+                   const int64_t* in_ids, const int64_t* excl_ids, float* scores_out, int64_t* ids_out,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched evaluation.  Replaces the per-user torchmetrics updates of update_metrics
+ * (xfmr_rec/lightning.py:149-187; metric set :289-306) for a batch of ranked result lists:
+ * ids [Q, k] int64 (-1 = empty slot), target_ids [Q, T] int64 (INT64_MIN = padding), target_vals [Q, T] fp32
+ * (graded relevance; relevant = value > 0).  per_query_out [Q, 6] fp32 = {ndcg, recall, precision, map,
+ * hit rate, mrr} at k (torchmetrics 1.8.2 definitions, a query without a relevant target scores 0);
+ * mean_out[6] (or NULL) = their means over the Q queries.
+ * ---------------------------------------------------------------------------------------------- */
+int xb_retrieval_metrics(int32_t num_queries, int32_t k, int32_t num_targets, const int64_t* ids,
+                         const int64_t* target_ids, const float* target_vals, float* per_query_out,
+                         float* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pair mask builder: bit (r, c) set  <=>  col_ids[c] == row_ids0[r]  or  col_ids[c] in row_id_lists[r, :].

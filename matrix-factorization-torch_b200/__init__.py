@@ -5,6 +5,8 @@ Public surface, mirroring the reference interfaces for this path:
 
 * the seven loss modules of ``xfmr_rec/losses.py`` + ``fused_losses`` (one contraction for any subset),
 * ``ItemProcessor`` / ``topk_search`` — exact top-k with the semantics of ``ItemProcessor.search``,
+* ``uniformity_loss`` / ``DirectAULoss`` / ``MAWULoss`` — the uniformity family the reference's README cites,
+* ``ItemProcessor.evaluate`` / ``retrieval_metrics`` — batched validation (search + the six ranking metrics),
 * ``hash_embedding_gather`` / ``HashEmbeddingBag`` — the hashed-embedding feeder,
 * ``distributed`` — global negatives (training) and catalog sharding (retrieval).
 """
@@ -26,10 +28,21 @@ from .losses import (
     PairwiseLogisticLoss,
     fused_losses,
 )
-from .retrieval import TOP_K, ItemProcessor, build_pair_mask, topk_merge, topk_search
+from .retrieval import (
+    METRIC_NAMES,
+    TOP_K,
+    ItemProcessor,
+    build_pair_mask,
+    retrieval_metrics,
+    topk_filter,
+    topk_merge,
+    topk_search,
+)
+from .uniformity import DirectAULoss, MAWULoss, UniformityLoss, uniformity_loss
 
 __all__ = [
     "ALL_LOSSES",
+    "METRIC_NAMES",
     "LIB_PATH",
     "LOSS_CLASSES",
     "LOSS_SLOTS",
@@ -37,13 +50,16 @@ __all__ = [
     "AlignmentContrastiveLoss",
     "AlignmentLoss",
     "ContrastiveLoss",
+    "DirectAULoss",
     "EmbeddingLoss",
     "HashEmbeddingBag",
     "InfomationNoiseContrastiveEstimationLoss",
     "ItemProcessor",
+    "MAWULoss",
     "MutualInformationNeuralEstimationLoss",
     "PairwiseHingeLoss",
     "PairwiseLogisticLoss",
+    "UniformityLoss",
     "XbError",
     "build_pair_mask",
     "distributed",
@@ -51,6 +67,9 @@ __all__ = [
     "hash_embedding_gather",
     "hash_indices",
     "launch_count",
+    "retrieval_metrics",
+    "topk_filter",
     "topk_merge",
     "topk_search",
+    "uniformity_loss",
 ]

@@ -50,6 +50,19 @@ class LossDesc(ctypes.Structure):
     ]
 
 
+class UniformityDesc(ctypes.Structure):
+    """``xb_uniformity_desc`` (include/xfmr_b200.h)."""
+
+    _fields_ = [
+        ("n", ctypes.c_int32),
+        ("dim", ctypes.c_int32),
+        ("in_dtype", ctypes.c_int32),
+        ("compute", ctypes.c_int32),
+        ("t", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 class TopkDesc(ctypes.Structure):
     """``xb_topk_desc`` (include/xfmr_b200.h)."""
 
@@ -79,6 +92,11 @@ SIGNATURES = {
     "xb_loss_workspace_bytes": (_sz, [ctypes.POINTER(LossDesc)]),
     "xb_loss_forward": (_i32, [ctypes.POINTER(LossDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xb_loss_backward": (_i32, [ctypes.POINTER(LossDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xb_uniformity_workspace_bytes": (_sz, [ctypes.POINTER(UniformityDesc)]),
+    "xb_uniformity_forward": (_i32, [ctypes.POINTER(UniformityDesc), _vp, _vp, _vp, _sz, _vp]),
+    "xb_uniformity_backward": (_i32, [ctypes.POINTER(UniformityDesc), _vp, _vp, _vp, _sz, _vp]),
+    "xb_topk_filter": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "xb_retrieval_metrics": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xb_topk_workspace_bytes": (_sz, [ctypes.POINTER(TopkDesc)]),
     "xb_mask_words": (_i32, [_i32]),
     "xb_topk_search": (_i32, [ctypes.POINTER(TopkDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

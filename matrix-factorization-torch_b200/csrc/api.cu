@@ -415,7 +415,7 @@ static SweepParams base_params(int nR, int nC, int kp, int parts, const SweepPla
 
 template <typename T>
 static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const float* d_losses, T* dq, T* di,
-                               uint8_t* ws, cudaStream_t st) {
+                               uint8_t* ws, cudaStream_t st, bool skip_items = false) {
   int rc;
   const int B = desc->batch, N = desc->num_items, d = desc->dim;
   const int lm = sweep_lm_from_mask(desc->loss_mask);
@@ -478,7 +478,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     }
     nq = w.gq.nchunks;
     nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
-    {  // dI sweep: rows = items, columns = queries (transposed mask)
+    if (!skip_items) {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
       p.use_aug = 1;
       p.rpar = reinterpret_cast<float*>(ws + w.ipar);
@@ -542,6 +542,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
       dq, gdiag, fq_part, fq_qg, fq_flag, lm);
   XB_LAUNCHED();
+  if (skip_items) return XB_OK;   // (uniformity: the column-side gradient equals the row-side one)
   grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(n_final_rows) * 32, 256), 256, 0, st>>>(
       n_final_rows, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
   XB_LAUNCHED();
@@ -776,6 +777,93 @@ int xb_loss_backward(const xb_loss_desc* desc, const float* d_losses, void* d_us
                                             static_cast<__nv_bfloat16*>(d_item), ws, st);
 }
 
+// ------------------------------------------------------------------------------------------------ uniformity
+namespace {
+struct UniformityWs {
+  xb_loss_desc ld;
+  LossWs lw;
+  size_t target, ids, losses, upstream, total;
+};
+int uniformity_layout(const xb_uniformity_desc* d, UniformityWs* u) {
+  if (d == nullptr) return fail(XB_ERR_INVALID_ARG, "desc is null");
+  if (d->n < 2) return fail(XB_ERR_INVALID_ARG, "uniformity needs n >= 2 rows (n=%d)", d->n);
+  if (!(d->t > 0.f)) return fail(XB_ERR_INVALID_ARG, "uniformity needs t > 0");
+  xb_loss_desc& ld = u->ld;
+  memset(&ld, 0, sizeof(ld));
+  ld.batch = ld.num_items = d->n;
+  ld.dim = d->dim;
+  ld.in_dtype = d->in_dtype;
+  ld.compute = d->compute;
+  ld.loss_mask = 1u << XB_LOSS_MINE;
+  ld.sigma = 2.f * d->t;   // sigma * S_ij = -t |x_i - x_j|^2   (S = -|.|^2 / 2)
+  ld.margin = 0.f;
+  const int rc = check_loss_desc(&ld);
+  if (rc != XB_OK) return rc;
+  loss_ws_layout(&ld, &u->lw);
+  size_t off = align_up(u->lw.total, 256);
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  u->target = take(sizeof(float) * d->n);
+  u->ids = take(sizeof(long long) * d->n);
+  u->losses = take(sizeof(float) * 8);
+  u->upstream = take(sizeof(float) * 8);
+  u->total = off;
+  return XB_OK;
+}
+}  // namespace
+
+size_t xb_uniformity_workspace_bytes(const xb_uniformity_desc* desc) {
+  UniformityWs u;
+  return uniformity_layout(desc, &u) == XB_OK ? u.total : 0;
+}
+
+int xb_uniformity_forward(const xb_uniformity_desc* desc, const void* x, float* loss_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  UniformityWs u;
+  int rc = uniformity_layout(desc, &u);
+  if (rc != XB_OK) return rc;
+  if (!x || !loss_out || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (workspace_bytes < u.total) return fail(XB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, u.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int n = desc->n;
+  float* target = reinterpret_cast<float*>(ws + u.target);
+  long long* ids = reinterpret_cast<long long*>(ws + u.ids);
+  uniformity_inputs_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, target, ids);
+  XB_LAUNCHED();
+  // per-row log sum_{j != i} exp(-t |x_i - x_j|^2): the MINE statistic with rows = columns = x and distinct ids
+  rc = xb_loss_forward(&u.ld, x, x, target, reinterpret_cast<const int64_t*>(ids), nullptr, nullptr,
+                       reinterpret_cast<float*>(ws + u.losses), workspace, u.lw.total, stream);
+  if (rc != XB_OK) return rc;
+  // all-pairs reduction; leaves each row's share of the total in rowinfo[i].y, which the backward reads as w_i
+  uniformity_reduce_kernel<<<1, 1024, 0, st>>>(n, reinterpret_cast<const float4*>(ws + u.lw.rowstat),
+                                               reinterpret_cast<float4*>(ws + u.lw.rowinfo), loss_out);
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_uniformity_backward(const xb_uniformity_desc* desc, const float* d_loss, void* d_x, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  UniformityWs u;
+  int rc = uniformity_layout(desc, &u);
+  if (rc != XB_OK) return rc;
+  if (!d_loss || !d_x || !workspace) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (workspace_bytes < u.total) return fail(XB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, u.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* upstream = reinterpret_cast<float*>(ws + u.upstream);
+  uniformity_upstream_kernel<<<1, 32, 0, st>>>(d_loss, upstream);
+  XB_LAUNCHED();
+  if (desc->in_dtype == XB_DTYPE_F32)
+    return loss_backward_typed<float>(&u.ld, u.lw, upstream, static_cast<float*>(d_x), static_cast<float*>(nullptr), ws, st,
+                                      true);
+  return loss_backward_typed<__nv_bfloat16>(&u.ld, u.lw, upstream, static_cast<__nv_bfloat16*>(d_x),
+                                            static_cast<__nv_bfloat16*>(nullptr), ws, st, true);
+}
+
 // ------------------------------------------------------------------------------------------------ pair mask
 size_t xb_pair_mask_workspace_bytes(int32_t num_cols) {
   if (num_cols < 0) return 0;
@@ -934,6 +1022,37 @@ int xb_topk_merge(int32_t num_queries, int32_t num_lists, int32_t list_len, int3
       num_queries, num_lists * list_len, k, in_scores, reinterpret_cast<const long long*>(in_ids), scores_out,
       reinterpret_cast<long long*>(ids_out));
   XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_topk_filter(int32_t num_queries, int32_t list_len, int32_t k, int32_t excl_len, const float* in_scores,
+                   const int64_t* in_ids, const int64_t* excl_ids, float* scores_out, int64_t* ids_out, void* stream) {
+  if (num_queries <= 0 || list_len <= 0 || k <= 0 || excl_len < 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (!in_scores || !in_ids || !scores_out || !ids_out || (excl_len > 0 && !excl_ids))
+    return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  if (list_len < k) return fail(XB_ERR_INVALID_ARG, "list_len %d < k %d", list_len, k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  topk_filter_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
+      num_queries, list_len, k, excl_len, in_scores, reinterpret_cast<const long long*>(in_ids),
+      reinterpret_cast<const long long*>(excl_ids), scores_out, reinterpret_cast<long long*>(ids_out));
+  XB_LAUNCHED();
+  return XB_OK;
+}
+
+int xb_retrieval_metrics(int32_t num_queries, int32_t k, int32_t num_targets, const int64_t* ids,
+                         const int64_t* target_ids, const float* target_vals, float* per_query_out, float* mean_out,
+                         void* stream) {
+  if (num_queries <= 0 || k <= 0 || num_targets <= 0) return fail(XB_ERR_INVALID_ARG, "bad sizes");
+  if (!ids || !target_ids || !target_vals || !per_query_out) return fail(XB_ERR_INVALID_ARG, "null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  retrieval_metrics_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
+      num_queries, k, num_targets, reinterpret_cast<const long long*>(ids),
+      reinterpret_cast<const long long*>(target_ids), target_vals, per_query_out);
+  XB_LAUNCHED();
+  if (mean_out != nullptr) {
+    retrieval_metrics_mean_kernel<<<1, 256, 0, st>>>(num_queries, per_query_out, mean_out);
+    XB_LAUNCHED();
+  }
   return XB_OK;
 }
 

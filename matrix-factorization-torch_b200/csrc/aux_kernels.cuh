@@ -376,6 +376,66 @@ __global__ void loss_reduce2_kernel(int nblk, const double* __restrict__ partial
 }
 
 // ------------------------------------------------------------------------------------------------
+// Uniformity (xb_uniformity_*): the loss forward runs as MINE with rows = columns = x, unit targets and
+// distinct ids (only the diagonal masked), so rowstat[i].y = log2 sum_{j != i} 2^(L2_ij).  The reduction below
+// merges the rows into LSE2 = log2 sum_i 2^(lse_i), writes loss = ln2 LSE2 - log(n (n - 1)) and replaces each
+// row's weight rowinfo[i].y by its share 2^(lse_i - LSE2) of the total, which is exactly the per-row factor
+// of d loss / d L_ij = 2^(L2_ij - LSE2) = w_i * softmax_i(j) that the MINE backward applies.
+// ------------------------------------------------------------------------------------------------
+__global__ void uniformity_inputs_kernel(int n, float* __restrict__ target, long long* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  target[i] = 1.f;
+  ids[i] = i + 1;
+}
+
+__global__ void __launch_bounds__(1024) uniformity_reduce_kernel(int n, const float4* __restrict__ rowstat,
+                                                                 float4* __restrict__ rowinfo,
+                                                                 float* __restrict__ loss_out) {
+  __shared__ float s_mx[1024];
+  __shared__ float s_se[1024];
+  const int tid = threadIdx.x;
+  float mx = -INFINITY, se = 0.f;
+  for (int i = tid; i < n; i += 1024) {
+    const float l = rowstat[i].y;
+    if (l == -INFINITY) continue;
+    if (l > mx) { se = se * exp2f(mx - l) + 1.f; mx = l; }
+    else se += exp2f(l - mx);
+  }
+  s_mx[tid] = mx;
+  s_se[tid] = se;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {   // fixed-shape tree: deterministic
+    if (tid < o) {
+      const float am = s_mx[tid], bm = s_mx[tid + o], as = s_se[tid], bs = s_se[tid + o];
+      const float hi = fmaxf(am, bm);
+      s_se[tid] = (as > 0.f ? as * exp2f(am - hi) : 0.f) + (bs > 0.f ? bs * exp2f(bm - hi) : 0.f);
+      s_mx[tid] = hi;
+    }
+    __syncthreads();
+  }
+  const float tot = s_se[0] > 0.f ? s_mx[0] + log2f(s_se[0]) : -INFINITY;
+  if (tid == 0) {
+    const double pairs = static_cast<double>(n) * static_cast<double>(n - 1);
+    loss_out[0] = tot == -INFINITY ? -INFINITY : static_cast<float>(static_cast<double>(tot) * 0.6931471805599453 - log(pairs));
+  }
+  for (int i = tid; i < n; i += 1024) {
+    const float l = rowstat[i].y;
+    const float w = (l == -INFINITY || tot == -INFINITY) ? 0.f : exp2f(l - tot);
+    float4 ri = rowinfo[i];
+    ri.y = w;
+    ri.z = w;
+    rowinfo[i] = ri;
+  }
+}
+
+// upstream gradient of the uniformity in the MINE slot; the factor 2 is the column-side gradient (see api.cu)
+__global__ void uniformity_upstream_kernel(const float* __restrict__ d_loss, float* __restrict__ u7) {
+  const int l = threadIdx.x;
+  if (l < 8) u7[l] = l == 4 ? 2.f * d_loss[0] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward.  Upstream gradients u[7] (output order) fold into per-loss coefficients
 //   uA = u0 + u2 (alignment), uC = u1 + u2, uI = u3, uM = u4, uH = u5, uL = u6.
 // Per query:  k_l = a * u_l * w (/ cnt for the mean losses), off_l as in sweep.cuh, where a = sigma*sign.
@@ -786,6 +846,123 @@ __global__ void pairs_select_kernel(int Q, int L, int k, const float* __restrict
       scores_out[static_cast<size_t>(row) * k + rank] = si;
       ids_out[static_cast<size_t>(row) * k + rank] = idi;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse exclusion lists (xb_topk_filter): a ranked list of L >= k + (excluded ids of the query) candidates
+// minus the excluded ids, first k kept in order.  One warp per query, 32 candidates per round.
+// ------------------------------------------------------------------------------------------------
+__global__ void topk_filter_kernel(int Q, int L, int k, int E, const float* __restrict__ scores,
+                                   const long long* __restrict__ ids, const long long* __restrict__ excl,
+                                   float* __restrict__ scores_out, long long* __restrict__ ids_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= Q) return;
+  const float* s = scores + static_cast<size_t>(row) * L;
+  const long long* id = ids + static_cast<size_t>(row) * L;
+  const long long* ex = excl + static_cast<size_t>(row) * E;
+  int kept = 0;
+  for (int i0 = 0; i0 < L && kept < k; i0 += 32) {
+    const int i = i0 + lane;
+    const long long idi = i < L ? id[i] : -1;
+    bool keep = idi >= 0;
+    if (keep)
+      for (int e = 0; e < E; ++e) keep = keep && ex[e] != idi;   // (padding is INT64_MIN: never an id)
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int pos = kept + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < k) {
+      scores_out[static_cast<size_t>(row) * k + pos] = s[i];
+      ids_out[static_cast<size_t>(row) * k + pos] = idi;
+    }
+    kept += __popc(m);
+  }
+  for (int j = min(kept, k) + lane; j < k; j += 32) {
+    scores_out[static_cast<size_t>(row) * k + j] = -INFINITY;
+    ids_out[static_cast<size_t>(row) * k + j] = -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ranking metrics of a batch of result lists against graded targets (xb_retrieval_metrics): the six
+// torchmetrics.retrieval metrics the reference logs at top_k (xfmr_rec/lightning.py:149-187, :289-306), per
+// query {ndcg, recall, precision, map, hit rate, mrr}.  One warp per query.  Definitions (torchmetrics 1.8.2,
+// binary relevance = value > 0, linear gain, discount 1 / log2(rank + 1), a query without a relevant target
+// scores 0 everywhere):
+//   ndcg = DCG@k(result order) / DCG@k(targets by value desc)     recall = hits / #relevant targets
+//   precision = hits / k      map = mean over hits of (hits so far / rank)      mrr = 1 / rank of the first hit
+// ------------------------------------------------------------------------------------------------
+__global__ void retrieval_metrics_kernel(int Q, int k, int T, const long long* __restrict__ ids,
+                                         const long long* __restrict__ target_ids,
+                                         const float* __restrict__ target_vals, float* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= Q) return;
+  const long long* rid = ids + static_cast<size_t>(row) * k;
+  const long long* tid = target_ids + static_cast<size_t>(row) * T;
+  const float* tv = target_vals + static_cast<size_t>(row) * T;
+  // targets: number of relevant ones and the ideal DCG (rank of a target = targets that sort before it)
+  float idcg = 0.f, nrel = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    if (tid[t] == EMPTY_KEY) continue;
+    const float v = tv[t];
+    nrel += v > 0.f ? 1.f : 0.f;
+    int rank = 0;
+    for (int u = 0; u < T; ++u) {
+      if (tid[u] == EMPTY_KEY) continue;
+      const float vu = tv[u];
+      rank += (vu > v || (vu == v && u < t)) ? 1 : 0;
+    }
+    if (rank < k) idcg += v / log2f(static_cast<float>(rank) + 2.f);
+  }
+  idcg = warp_sum(idcg);
+  nrel = warp_sum(nrel);
+  // result list in rank order, 32 ranks per round
+  float dcg = 0.f, ap = 0.f;
+  int hits = 0, first = -1;
+  for (int r0 = 0; r0 < k; r0 += 32) {
+    const int r = r0 + lane;
+    const long long idr = r < k ? rid[r] : -1;
+    float gain = 0.f;
+    bool found = false;
+    if (idr >= 0)
+      for (int t = 0; t < T && !found; ++t)
+        if (tid[t] == idr) { gain = tv[t]; found = true; }
+    const bool rel = found && gain > 0.f;
+    if (found) dcg += gain / log2f(static_cast<float>(r) + 2.f);
+    const unsigned m = __ballot_sync(0xffffffffu, rel);
+    if (rel) ap += static_cast<float>(hits + __popc(m & ((2u << lane) - 1u))) / static_cast<float>(r + 1);
+    if (first < 0 && m != 0u) first = r0 + __ffs(m) - 1;
+    hits += __popc(m);
+  }
+  dcg = warp_sum(dcg);
+  ap = warp_sum(ap);
+  if (lane != 0) return;
+  float* o = out + static_cast<size_t>(row) * 6;
+  const bool any = nrel > 0.f;
+  o[0] = (any && idcg > 0.f) ? dcg / idcg : 0.f;
+  o[1] = any ? static_cast<float>(hits) / nrel : 0.f;
+  o[2] = any ? static_cast<float>(hits) / static_cast<float>(k) : 0.f;
+  o[3] = (any && hits > 0) ? ap / static_cast<float>(hits) : 0.f;
+  o[4] = (any && hits > 0) ? 1.f : 0.f;
+  o[5] = (any && first >= 0) ? 1.f / static_cast<float>(first + 1) : 0.f;
+}
+
+// mean over the queries of each of the 6 columns: fixed-shape fp64 reduction, one block
+__global__ void __launch_bounds__(256) retrieval_metrics_mean_kernel(int Q, const float* __restrict__ per_query,
+                                                                     float* __restrict__ mean_out) {
+  __shared__ double sh[256];
+  for (int m = 0; m < 6; ++m) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < Q; i += 256) acc += static_cast<double>(per_query[static_cast<size_t>(i) * 6 + m]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) mean_out[m] = static_cast<float>(sh[0] / static_cast<double>(Q));
+    __syncthreads();
   }
 }
 

@@ -155,6 +155,79 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.T
     return out_s, out_i
 
 
+def topk_filter(
+    scores: torch.Tensor, ids: torch.Tensor, exclude: torch.Tensor, k: int
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """Drop the ids listed in ``exclude [Q, E]`` (padded with ``PAD_ID``) from ranked lists ``[Q, L]``; keep k.
+
+    ``xb_topk_filter``: with ``L >= k + E`` this equals removing the excluded items BEFORE ranking, the
+    ``prefilter=True`` semantics of ``ItemProcessor.search`` (data/lightning.py:247-252), without a dense
+    ``Q x N`` exclusion mask.
+    """
+    device = _lib.require_cuda(scores, ids, exclude)
+    scores = scores.to(torch.float32).contiguous()
+    ids = ids.to(torch.int64).contiguous()
+    exclude = exclude.to(torch.int64).contiguous()
+    num_queries, length = scores.shape
+    if exclude.dim() != 2 or exclude.size(0) != num_queries:  # noqa: PLR2004
+        msg = f"exclude must be [{num_queries}, E], got {tuple(exclude.shape)}"
+        raise ValueError(msg)
+    with torch.cuda.device(device):
+        out_s = torch.empty(num_queries, k, dtype=torch.float32, device=device)
+        out_i = torch.empty(num_queries, k, dtype=torch.int64, device=device)
+        status = _lib.lib.xb_topk_filter(
+            num_queries, length, k, exclude.size(1), scores.data_ptr(), ids.data_ptr(),
+            exclude.data_ptr() if exclude.numel() else None, out_s.data_ptr(), out_i.data_ptr(),
+            _lib.stream_ptr(device),
+        )
+    _lib.check(status, "xb_topk_filter")
+    return out_s, out_i
+
+
+METRIC_NAMES = (
+    "RetrievalNormalizedDCG",
+    "RetrievalRecall",
+    "RetrievalPrecision",
+    "RetrievalMAP",
+    "RetrievalHitRate",
+    "RetrievalMRR",
+)  # xfmr_rec/lightning.py:296-301, in the column order of xb_retrieval_metrics
+
+
+def retrieval_metrics(
+    ids: torch.Tensor, target_ids: torch.Tensor, target_vals: torch.Tensor
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """``(per_query [Q, 6], mean [6])`` ranking metrics at ``k = ids.size(1)`` (``xb_retrieval_metrics``).
+
+    ``ids [Q, k]`` ranked result lists (-1 = empty), ``target_ids [Q, T]`` padded with ``PAD_ID``,
+    ``target_vals [Q, T]`` graded relevance.  Columns as ``METRIC_NAMES`` — what ``update_metrics``
+    (xfmr_rec/lightning.py:149-187) feeds torchmetrics one user at a time.
+    """
+    device = _lib.require_cuda(ids, target_ids, target_vals)
+    ids = ids.to(torch.int64).contiguous()
+    target_ids = target_ids.to(torch.int64).contiguous()
+    target_vals = target_vals.to(torch.float32).contiguous()
+    num_queries, k = ids.shape
+    if target_ids.shape != target_vals.shape or target_ids.dim() != 2 or target_ids.size(0) != num_queries:  # noqa: PLR2004
+        msg = f"targets must be [{num_queries}, T] ids and values, got {tuple(target_ids.shape)} / {tuple(target_vals.shape)}"
+        raise ValueError(msg)
+    with torch.cuda.device(device):
+        per_query = torch.empty(num_queries, len(METRIC_NAMES), dtype=torch.float32, device=device)
+        mean = torch.empty(len(METRIC_NAMES), dtype=torch.float32, device=device)
+        status = _lib.lib.xb_retrieval_metrics(
+            num_queries, k, target_ids.size(1), ids.data_ptr(), target_ids.data_ptr(), target_vals.data_ptr(),
+            per_query.data_ptr(), mean.data_ptr(), _lib.stream_ptr(device),
+        )
+    _lib.check(status, "xb_retrieval_metrics")
+    return per_query, mean
+
+
+def pad_id_lists(lists: Sequence[Sequence[int]], *, pad: int = _PAD_ID, dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """Ragged python lists -> ``[len(lists), max_len]`` tensor padded with ``pad`` (at least one column)."""
+    width = max(max((len(e) for e in lists), default=0), 1)
+    return torch.tensor([list(e) + [pad] * (width - len(e)) for e in lists], dtype=dtype)
+
+
 class ItemProcessor:
     """Exact-search stand-in for ``xfmr_rec.data.lightning.ItemProcessor`` (search side only).
 
@@ -190,27 +263,46 @@ class ItemProcessor:
         self.item_text = item_text
         return self
 
-    def _exclusion_mask(self, exclude: torch.Tensor | Sequence[Sequence[int]] | None, num_queries: int) -> torch.Tensor | None:
+    # exclusion lists go through a dense [Q, N] bit mask (exact for any list length) while that mask is small, and
+    # through a post-filter of the k + E best otherwise (exact while k + E <= MAX_K) — see _exclusions
+    DENSE_MASK_BYTES = 256 << 20
+    MAX_K = 256
+
+    def _exclusions(
+        self, exclude: torch.Tensor | Sequence[Sequence[int]] | None, num_queries: int, top_k: int
+    ) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        """``(dense bit mask, sparse id lists)`` — at most one of them is not None."""
         if exclude is None:
-            return None
+            return None, None
         assert self.embeddings is not None
         device = self.embeddings.device
         if not isinstance(exclude, torch.Tensor):
-            width = max((len(e) for e in exclude), default=0)
-            if width == 0:
-                return None
-            rows = [list(e) + [_PAD_ID] * (width - len(e)) for e in exclude]
-            exclude = torch.tensor(rows, dtype=torch.int64)
+            if max((len(e) for e in exclude), default=0) == 0:
+                return None, None
+            exclude = pad_id_lists(exclude)
         if exclude.numel() == 0:
-            return None
+            return None, None
         if exclude.size(0) != num_queries:
             msg = f"one exclusion list per query expected: {exclude.size(0)} lists for {num_queries} queries"
             raise ValueError(msg)
+        exclude = exclude.to(device)
+        num_items = self.embeddings.size(0)
+        mask_bytes = (-(-num_queries // 128) * 128) * (-(-num_items // 128) * 16)
+        sparse_ok = top_k + exclude.size(1) <= self.MAX_K
+        if mask_bytes > self.DENSE_MASK_BYTES:
+            if not sparse_ok:
+                msg = (
+                    f"exclusion lists of {exclude.size(1)} ids with top_k={top_k} need a dense {mask_bytes >> 20} MiB mask "
+                    f"(limit {self.DENSE_MASK_BYTES >> 20} MiB) or top_k + list length <= {self.MAX_K}; search in smaller "
+                    "query batches"
+                )
+                raise ValueError(msg)
+            return None, exclude
         col_ids = self.item_ids
         if col_ids is None:
-            col_ids = torch.arange(self.embeddings.size(0), dtype=torch.int64, device=device)
-        mask, _ = build_pair_mask(col_ids, exclude.to(device))
-        return mask
+            col_ids = torch.arange(num_items, dtype=torch.int64, device=device)
+        mask, _ = build_pair_mask(col_ids, exclude)
+        return mask, None
 
     def search_batch(
         self,
@@ -226,10 +318,41 @@ class ItemProcessor:
         if queries.dim() == 1:
             queries = queries[None, :]
         queries = queries.to(self.embeddings.device)
-        mask = self._exclusion_mask(exclude_item_ids, queries.size(0))
+        mask, sparse = self._exclusions(exclude_item_ids, queries.size(0), top_k)
+        if sparse is not None:
+            fetch = top_k + sparse.size(1)
+            scores, ids = topk_search(queries, self.embeddings, fetch, item_ids=self.item_ids, compute=self.compute)
+            return topk_filter(scores, ids, sparse, top_k)
         return topk_search(
             queries, self.embeddings, top_k, item_ids=self.item_ids, excl_mask=mask, compute=self.compute
         )
+
+    def evaluate(
+        self,
+        embedding: torch.Tensor,
+        target_ids: torch.Tensor | Sequence[Sequence[int]],
+        target_vals: torch.Tensor | Sequence[Sequence[float]],
+        exclude_item_ids: torch.Tensor | Sequence[Sequence[int]] | None = None,
+        top_k: int = TOP_K,
+    ) -> dict[str, torch.Tensor]:
+        """Batched validation: search + the six ranking metrics of ``update_metrics`` for all users at once.
+
+        The reference evaluates one user per step (``validation_step`` -> ``update_metrics`` -> ``recommend`` ->
+        ``search``, xfmr_rec/lightning.py:149-206, history excluded at :88-89).  Returns ``{metric name: mean over
+        users}`` (0-d tensors on the GPU, names as torchmetrics' classes, :296-301) plus ``"per_query"`` ``[Q, 6]``.
+        """
+        _scores, ids = self.search_batch(embedding, exclude_item_ids, top_k)
+        device = ids.device
+        if not isinstance(target_ids, torch.Tensor):
+            if [len(e) for e in target_ids] != [len(e) for e in target_vals]:
+                msg = "target_ids and target_vals must be lists of equal lengths, row by row"
+                raise ValueError(msg)
+            target_vals = pad_id_lists(target_vals, pad=0, dtype=torch.float32)
+            target_ids = pad_id_lists(target_ids)
+        per_query, mean = retrieval_metrics(ids, target_ids.to(device), torch.as_tensor(target_vals).to(device))
+        out = {name: mean[i] for i, name in enumerate(METRIC_NAMES)}
+        out["per_query"] = per_query
+        return out
 
     def search(
         self,

@@ -1,0 +1,136 @@
+"""Uniformity / DirectAU / MAWU on the sweep kernel against the published definitions (``oracle/losses_oracle.py``).
+
+Parity is unpinned by the reference (it only cites the papers, README.md:22-25).  Tolerance: the north star's
+rel 1e-3 for losses and gradients (norm-wise), fp32 accumulation.
+"""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+from helpers import bf16_round, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def unit_rows(n: int, d: int, seed: int, spread: float = 1.0) -> torch.Tensor:
+    gen = torch.Generator().manual_seed(seed)
+    base = torch.randn(1, d, generator=gen)
+    return torch.nn.functional.normalize(base + spread * torch.randn(n, d, generator=gen), dim=-1)
+
+
+def oracle_uniformity(x: torch.Tensor, t: float) -> tuple[float, torch.Tensor]:
+    from oracle import losses_oracle  # noqa: PLC0415
+
+    x64 = x.double().requires_grad_(True)
+    loss = losses_oracle.uniformity(x64, t)
+    (grad,) = torch.autograd.grad(loss, x64)
+    return float(loss), grad
+
+
+@pytest.mark.parametrize(("n", "d", "t", "spread"), [
+    (2, 8, 2.0, 1.0),         # a single pair
+    (48, 32, 2.0, 1.0),
+    (257, 64, 2.0, 0.3),      # ragged tiles, clustered rows
+    (1000, 128, 2.0, 1.0),
+    (1024, 64, 0.5, 1.0),
+    (3000, 48, 5.0, 0.1),     # d not a multiple of 64, several row blocks and column chunks
+])
+def test_uniformity_fp32(n: int, d: int, t: float, spread: float) -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    x = unit_rows(n, d, n + d, spread)
+    want, want_grad = oracle_uniformity(x, t)
+    xc = x.cuda().requires_grad_(True)
+    loss = xfmr_b200.uniformity_loss(xc, t)
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    (grad,) = torch.autograd.grad(loss, xc)
+    e_loss = abs(float(loss) - want) / max(abs(want), 1e-6)
+    e_grad = rel_err(grad, want_grad)
+    print(f"uniformity n={n} d={d} t={t}: loss {float(loss):.6f} vs {want:.6f} rel {e_loss:.2e} grad {e_grad:.2e}")
+    assert e_loss < RTOL
+    assert e_grad < RTOL
+
+
+def test_uniformity_unnormalised_rows_and_duplicates() -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    gen = torch.Generator().manual_seed(3)
+    x = 0.7 * torch.randn(300, 64, generator=gen)
+    x[17] = x[5]   # duplicate rows are distinct samples (distance 0), not masked
+    x[200] = x[5]
+    want, want_grad = oracle_uniformity(x, 2.0)
+    xc = x.cuda().requires_grad_(True)
+    loss = xfmr_b200.UniformityLoss(t=2.0)(xc)
+    (grad,) = torch.autograd.grad(loss, xc)
+    assert abs(float(loss) - want) / abs(want) < RTOL
+    assert rel_err(grad, want_grad) < RTOL
+
+
+def test_uniformity_bf16_io() -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    x = unit_rows(2048, 128, 11)
+    want, want_grad = oracle_uniformity(bf16_round(x), 2.0)
+    xc = x.cuda().bfloat16().requires_grad_(True)
+    loss = xfmr_b200.uniformity_loss(xc, 2.0)
+    (grad,) = torch.autograd.grad(loss, xc)
+    assert grad.dtype == torch.bfloat16
+    assert abs(float(loss) - want) / abs(want) < RTOL
+    assert rel_err(grad.float(), want_grad) < 2.0**-8   # gradients are rounded to bf16 on the way out
+
+
+def test_uniformity_upstream_gradient_scales() -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    x = unit_rows(500, 64, 5).cuda()
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    (ga,) = torch.autograd.grad(xfmr_b200.uniformity_loss(a), a)
+    (gb,) = torch.autograd.grad(-3.5 * xfmr_b200.uniformity_loss(b), b)
+    assert rel_err(gb, -3.5 * ga) < 1e-6
+
+
+def test_uniformity_rejects_bad_input() -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    with pytest.raises(ValueError, match="two rows"):
+        xfmr_b200.uniformity_loss(torch.zeros(1, 8, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.uniformity_loss(torch.zeros(4, 8))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32])
+def test_directau_and_mawu(dtype: torch.dtype) -> None:
+    import xfmr_b200  # noqa: PLC0415
+    from oracle import losses_oracle  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    inp = synthetic.make_loss_inputs(384, 900, 64, 4, n_catalog=700, seed=2)
+    target = inp["target"].abs() + 0.5
+    dev = torch.device("cuda:0")
+
+    def run(module, oracle_fn, **extra):  # noqa: ANN001, ANN003, ANN202
+        q = inp["user_embed"].to(dev, dtype).requires_grad_(True)
+        v = inp["item_embed"].to(dev, dtype).requires_grad_(True)
+        loss = module(q, v, target.to(dev), item_idx=inp["item_idx"].to(dev), pos_idx=inp["pos_idx"].to(dev),
+                      **{k: t.to(dev) for k, t in extra.items()})
+        dq, dv = torch.autograd.grad(loss, (q, v))
+        q64 = inp["user_embed"].double().requires_grad_(True)
+        v64 = inp["item_embed"].double().requires_grad_(True)
+        want = oracle_fn(q64, v64, target.double(), **{k: t.double() for k, t in extra.items()})
+        rq, rv = torch.autograd.grad(want, (q64, v64))
+        assert abs(float(loss) - float(want)) / abs(float(want)) < RTOL, (float(loss), float(want))
+        assert rel_err(dq, rq) < RTOL
+        assert rel_err(dv, rv) < RTOL
+        assert float(dv[384:].abs().max()) == 0.0   # uniform negatives beyond the batch take no part
+
+    run(xfmr_b200.DirectAULoss(gamma=0.7, t=2.0), lambda q, v, t: losses_oracle.directau(q, v, t, gamma=0.7, t=2.0))
+    run(xfmr_b200.MAWULoss(gamma_user=0.4, gamma_item=1.3), lambda q, v, t: losses_oracle.mawu(q, v, t, gamma_user=0.4, gamma_item=1.3))
+    gen = torch.Generator().manual_seed(0)
+    margins = {"user_margin": 0.1 * torch.rand(384, generator=gen), "item_margin": 0.1 * torch.rand(384, generator=gen)}
+    run(xfmr_b200.MAWULoss(gamma_user=0.4, gamma_item=1.3),
+        lambda q, v, t, **m: losses_oracle.mawu(q, v, t, gamma_user=0.4, gamma_item=1.3, **m), **margins)
