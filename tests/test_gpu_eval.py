@@ -79,7 +79,7 @@ def targets_for(q: torch.Tensor, it: torch.Tensor, ids: np.ndarray, seed: int) -
             out.append({})                                                       # user without targets
             continue
         order = np.argsort(-full[r])
-        near = order[rng.choice(60, size=int(rng.integers(1, 12)), replace=False)]   # some will be retrieved
+        near = order[rng.choice(min(60, len(ids)), size=int(rng.integers(1, 12)), replace=False)]   # some will be retrieved
         far = rng.choice(len(ids), size=int(rng.integers(0, 8)), replace=False)
         t = {int(ids[j]): float(rng.integers(1, 6)) for j in np.concatenate([near, far])}
         if kind == 1:

@@ -28,7 +28,7 @@ def oracle_uniformity(x: torch.Tensor, t: float) -> tuple[float, torch.Tensor]:
     x64 = x.double().requires_grad_(True)
     loss = losses_oracle.uniformity(x64, t)
     (grad,) = torch.autograd.grad(loss, x64)
-    return float(loss), grad
+    return float(loss.detach()), grad
 
 
 @pytest.mark.parametrize(("n", "d", "t", "spread"), [
