@@ -7,12 +7,14 @@ Public surface, mirroring the reference interfaces for this path:
 * ``ItemProcessor`` / ``topk_search`` — exact top-k with the semantics of ``ItemProcessor.search``,
 * ``uniformity_loss`` / ``DirectAULoss`` / ``MAWULoss`` — the uniformity family the reference's README cites,
 * ``ItemProcessor.evaluate`` / ``retrieval_metrics`` — batched validation (search + the six ranking metrics),
+* ``GraphedLossStep`` — a loss step as one CUDA graph with a pipelined host-input feed,
 * ``hash_embedding_gather`` / ``HashEmbeddingBag`` — the hashed-embedding feeder,
 * ``distributed`` — global negatives (training) and catalog sharding (retrieval).
 """
 
 from . import distributed
 from ._lib import LIB_PATH, XbError, launch_count
+from .graphs import GraphedLossStep, StepResult
 from .hashing import HashEmbeddingBag, hash_embedding_gather, hash_indices
 from .losses import (
     ALL_LOSSES,
@@ -52,6 +54,7 @@ __all__ = [
     "ContrastiveLoss",
     "DirectAULoss",
     "EmbeddingLoss",
+    "GraphedLossStep",
     "HashEmbeddingBag",
     "InfomationNoiseContrastiveEstimationLoss",
     "ItemProcessor",
@@ -59,6 +62,7 @@ __all__ = [
     "MutualInformationNeuralEstimationLoss",
     "PairwiseHingeLoss",
     "PairwiseLogisticLoss",
+    "StepResult",
     "UniformityLoss",
     "XbError",
     "build_pair_mask",

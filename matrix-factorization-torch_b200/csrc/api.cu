@@ -285,6 +285,11 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
 constexpr int MINE_CAP = 256;    // largest candidate buffer per row for the mining sweep (workspace is sized for it)
 // actual buffer for a given number of kept entries
 static int mine_cap_for(int keep) {
+  static const int forced = [] {
+    const char* e = std::getenv("XB_MINE_CAP");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced >= 64 && forced <= MINE_CAP && (forced & (forced - 1)) == 0 && forced >= 2 * keep) return forced;
   int cap = 64;
   while (cap < 8 * keep + 32) cap <<= 1;   // (measured: compactions cost more than the candidates a fresher threshold saves)
   return cap < MINE_CAP ? cap : MINE_CAP;

@@ -460,11 +460,7 @@ __device__ __forceinline__ unsigned long long compact_select(unsigned long long*
     const int idx = i * 32 + lane;
     e[i] = idx < cnt ? buf[idx] : 0ull;
   }
-  auto warp_total = [](int c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    return c;
-  };
+  auto warp_total = [](int c) { return __reduce_add_sync(0xffffffffu, c); };   // one REDUX instead of a 5-step butterfly
   // phase 1: the keep-th largest KEY (high word): largest T with count(key >= T) >= keep
   uint32_t T = 0u;
   int c_ge = 0;

@@ -1,0 +1,131 @@
+"""CUDA-graph replay of a loss step with a pipelined host-input feed.
+
+The C-ABI entry points allocate nothing and never synchronise (``include/xfmr_b200.h``), so a module's
+forward + backward is capturable as one CUDA graph.  ``GraphedLossStep`` does the capture once for a fixed
+input shape and then serves steps from either device tensors or pinned host tensors:
+
+* host inputs are uploaded on a copy stream into one of two staging slots, so the upload of step ``i + 1`` runs
+  under the graph replay of step ``i`` (what a training loop's prefetching data loader does for the reference's
+  ``training_step``, ``xfmr_rec/lightning.py:189-192``);
+* the step's loss is copied back to pinned host memory asynchronously; ``StepResult.loss_value()`` waits for
+  that copy only, so a caller can read step ``i - 1`` while step ``i`` is in flight.
+
+Everything here is stream/graph plumbing around the module call; no arithmetic.
+"""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING
+
+import torch
+
+if TYPE_CHECKING:
+    from .losses import EmbeddingLoss
+
+_INPUT_KEYS = ("user_embed", "item_embed", "target", "item_idx", "pos_idx")
+
+
+class StepResult:
+    """Handle of one submitted step: static output tensors + the host copy of its loss."""
+
+    def __init__(self, step: GraphedLossStep, slot: int, done: torch.cuda.Event) -> None:
+        self._step = step
+        self._slot = slot
+        self._done = done
+
+    def loss_value(self) -> float:
+        """Host value of this step's loss (waits for the step's device -> host copy, not for later steps)."""
+        self._done.synchronize()
+        return float(self._step._loss_host[self._slot])  # noqa: SLF001
+
+    @property
+    def d_user(self) -> torch.Tensor:
+        """Static gradient buffer (overwritten by the next step)."""
+        return self._step.d_user
+
+    @property
+    def d_item(self) -> torch.Tensor:
+        return self._step.d_item
+
+
+class GraphedLossStep:
+    """``module(user_embed, item_embed, target, item_idx=, pos_idx=)`` + backward as one CUDA graph.
+
+    ``example`` fixes shapes and dtypes (a dict with the five input tensors on the GPU).  ``submit(inputs)``
+    takes a dict of the same tensors on the GPU or in (pinned) host memory.
+    """
+
+    def __init__(self, module: EmbeddingLoss, example: dict[str, torch.Tensor]) -> None:
+        device = example["user_embed"].device
+        if device.type != "cuda":
+            msg = "GraphedLossStep needs CUDA tensors as the example inputs; there is no CPU path"
+            raise RuntimeError(msg)
+        self.module = module
+        self.device = device
+        self.static = {k: example[k].detach().clone() for k in _INPUT_KEYS}
+        self.static["user_embed"].requires_grad_(True)
+        self.static["item_embed"].requires_grad_(True)
+        self._staging = [{k: torch.empty_like(example[k]) for k in _INPUT_KEYS} for _ in range(2)]
+        self._uploaded = [torch.cuda.Event() for _ in range(2)]
+        self._consumed: list[torch.cuda.Event | None] = [None, None]
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._copy_stream = torch.cuda.Stream(device=device)
+        self._next_slot = 0
+        self._pending: tuple[int, bool] | None = None
+
+        def step() -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+            s = self.static
+            loss = module(s["user_embed"], s["item_embed"], s["target"], item_idx=s["item_idx"], pos_idx=s["pos_idx"])
+            dq, dv = torch.autograd.grad(loss, (s["user_embed"], s["item_embed"]))
+            return loss, dq, dv
+
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.d_user, self.d_item = step()
+        torch.cuda.synchronize(device)
+
+    def prefetch(self, inputs: dict[str, torch.Tensor]) -> None:
+        """Start moving ``inputs`` into the next staging slot on the copy stream (returns at once)."""
+        if self._pending is not None:
+            msg = "a prefetched step is already waiting: call submit() first"
+            raise RuntimeError(msg)
+        slot = self._next_slot
+        consumed = self._consumed[slot]
+        with torch.cuda.stream(self._copy_stream):
+            if consumed is not None:
+                self._copy_stream.wait_event(consumed)  # the step that last read this slot has taken its copy
+            for k in _INPUT_KEYS:
+                self._staging[slot][k].copy_(inputs[k], non_blocking=True)
+            self._uploaded[slot].record(self._copy_stream)
+        self._pending = (slot, True)
+        self._next_slot = 1 - slot
+
+    def submit(self, inputs: dict[str, torch.Tensor] | None = None) -> StepResult:
+        """Run one step on ``inputs`` (or on the inputs given to the last ``prefetch``); returns at once."""
+        if self._pending is None:
+            if inputs is None:
+                msg = "nothing to run: give inputs or call prefetch() first"
+                raise RuntimeError(msg)
+            self.prefetch(inputs)
+        slot, _ = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._uploaded[slot])
+        with torch.no_grad():
+            for k in _INPUT_KEYS:
+                self.static[k].copy_(self._staging[slot][k], non_blocking=True)
+        consumed = torch.cuda.Event()
+        consumed.record(cur)
+        self._consumed[slot] = consumed
+        self.graph.replay()
+        self._loss_host[slot : slot + 1].copy_(self.loss.detach().reshape(1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return StepResult(self, slot, done)

@@ -241,3 +241,35 @@ def test_all_rows_masked_and_zero_targets() -> None:
     # zero targets: the whole batch contributes nothing
     z = xfmr_b200.fused_losses(q, v, torch.zeros(4, device=dev), item_idx=torch.arange(1, 7, device=dev), pos_idx=pos_idx)
     assert torch.all(z == 0)
+
+
+def test_graphed_step_matches_eager_and_takes_host_inputs() -> None:
+    """``GraphedLossStep``: CUDA-graph replay with the double-buffered host feed gives the eager results, step after step."""
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    dev = torch.device("cuda:0")
+    batches = [synthetic.make_loss_inputs(300, 1000, 64, 6, n_catalog=800, seed=s) for s in range(4)]
+    module = xfmr_b200.InfomationNoiseContrastiveEstimationLoss(sigma=3.0)
+    keys = ("user_embed", "item_embed", "target", "item_idx", "pos_idx")
+    stepper = xfmr_b200.GraphedLossStep(module, {k: batches[0][k].to(dev) for k in keys})
+    results = []
+    hosts = [{k: b[k].pin_memory() for k in keys} for b in batches]
+    stepper.prefetch(hosts[0])
+    for i in range(len(batches)):
+        res = stepper.submit()
+        got_dq, got_dv = res.d_user.clone(), res.d_item.clone()   # static buffers: copy before the next step
+        if i + 1 < len(batches):
+            stepper.prefetch(hosts[i + 1])
+        results.append((res.loss_value(), got_dq, got_dv))
+    for b, (loss, dq, dv) in zip(batches, results, strict=True):
+        q = b["user_embed"].to(dev).requires_grad_(True)
+        v = b["item_embed"].to(dev).requires_grad_(True)
+        want = module(q, v, b["target"].to(dev), item_idx=b["item_idx"].to(dev), pos_idx=b["pos_idx"].to(dev))
+        wq, wv = torch.autograd.grad(want, (q, v))
+        assert loss == pytest.approx(float(want.detach()), rel=1e-6)
+        assert torch.equal(dq, wq)
+        assert torch.equal(dv, wv)
+    # device inputs go through the same path
+    res = stepper.submit({k: batches[1][k].to(dev) for k in keys})
+    assert res.loss_value() == pytest.approx(results[1][0], rel=1e-6)
