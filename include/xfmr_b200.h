@@ -54,6 +54,10 @@ extern "C" {
 #define XB_LOSS_PAIRWISE_LOGISTIC 6     /* PairwiseLogisticLoss                           :352-354 */
 #define XB_NUM_LOSSES 7
 
+/* negative mining order when 0 < num_negatives < N */
+#define XB_MINING_SEMI_HARD 0  /* semi_hard_mining (losses.py:134-162) — what every reference loss calls */
+#define XB_MINING_HARD 1       /* hard_mining (losses.py:112-132): the K largest logits; defined, never called there */
+
 /* ------------------------------------------------------------------------------------------------
  * Losses.  Replaces EmbeddingLoss.forward(user_embed, item_embed, target, *, item_idx, pos_idx)
  * (xfmr_rec/losses.py:39-52) and its autograd backward for every class selected in loss_mask, with one
@@ -71,7 +75,7 @@ typedef struct xb_loss_desc {
   float sigma;            /* losses.py:31                                                     */
   float margin;           /* losses.py:32                                                     */
   int32_t has_log_q;      /* 1: subtract log_q[j] from every logit (LogQ correction; extension) */
-  int32_t reserved;
+  int32_t mining;         /* XB_MINING_*: which K columns num_negatives keeps                  */
 } xb_loss_desc;
 
 size_t xb_loss_workspace_bytes(const xb_loss_desc* desc);

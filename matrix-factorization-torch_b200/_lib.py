@@ -23,6 +23,8 @@ XB_DTYPE_BF16 = 1
 XB_COMPUTE_BF16 = 0
 XB_COMPUTE_SPLIT = 1
 XB_NUM_LOSSES = 7
+XB_MINING_SEMI_HARD = 0
+XB_MINING_HARD = 1
 
 ERROR_NAMES = {-1: "invalid argument", -2: "unsupported shape", -3: "workspace too small", -4: "CUDA error"}
 
@@ -46,7 +48,7 @@ class LossDesc(ctypes.Structure):
         ("sigma", ctypes.c_float),
         ("margin", ctypes.c_float),
         ("has_log_q", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("mining", ctypes.c_int32),
     ]
 
 
@@ -188,6 +190,16 @@ def compute_code(compute: str | None, dtype: torch.dtype) -> int:
     if compute in ("split", "fp32", "float32"):
         return XB_COMPUTE_SPLIT
     msg = f"compute must be None, 'bf16' or 'fp32', got {compute!r}"
+    raise ValueError(msg)
+
+
+def mining_code(mining: str) -> int:
+    """``"semi_hard"`` (``semi_hard_mining``, what the reference losses call) or ``"hard"`` (``hard_mining``)."""
+    if mining in ("semi_hard", "semi-hard"):
+        return XB_MINING_SEMI_HARD
+    if mining == "hard":
+        return XB_MINING_HARD
+    msg = f"mining must be 'semi_hard' or 'hard', got {mining!r}"
     raise ValueError(msg)
 
 

@@ -382,6 +382,7 @@ static int check_loss_desc(const xb_loss_desc* d) {
   if (d->in_dtype != XB_DTYPE_F32 && d->in_dtype != XB_DTYPE_BF16) return fail(XB_ERR_INVALID_ARG, "bad in_dtype");
   if (d->compute != XB_COMPUTE_BF16 && d->compute != XB_COMPUTE_SPLIT) return fail(XB_ERR_INVALID_ARG, "bad compute");
   if ((d->loss_mask & ~0x7fu) != 0 || d->loss_mask == 0) return fail(XB_ERR_INVALID_ARG, "bad loss_mask");
+  if (d->mining != XB_MINING_SEMI_HARD && d->mining != XB_MINING_HARD) return fail(XB_ERR_INVALID_ARG, "bad mining mode");
   const int kp = cdiv(d->dim, KBLK) * KBLK;
   if (kp > 256) return fail(XB_ERR_UNSUPPORTED, "dim %d > 256 is not supported", d->dim);
   if (d->num_negatives > MINE_KMAX && d->num_negatives < d->num_items)
@@ -728,8 +729,12 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
       p.cap = mine_cap_for(w.Kf);
       p.keep = w.Kf;
-      for (int side = 0; side < 2; ++side) {
-        p.topk_mining = 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
+      const bool hard = desc->mining == XB_MINING_HARD;
+      // hard mining has one continuous order (logit descending): one sweep; the second half of `sel` stays empty
+      if (hard)
+        XB_CUDA(cudaMemsetAsync(ws + w.sel, 0, sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w.Kf, st));
+      for (int side = 0; side < (hard ? 1 : 2); ++side) {
+        p.topk_mining = hard ? 3 : 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
             B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), p.cap, w.Kf, p.cand, p.cand_cnt,
@@ -745,7 +750,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
           reinterpret_cast<__nv_bfloat16*>(ws + w.qprep), reinterpret_cast<__nv_bfloat16*>(ws + w.iprep),
           reinterpret_cast<float4*>(ws + w.qfwd), reinterpret_cast<float2*>(ws + w.ipar),
           reinterpret_cast<float4*>(ws + w.rowinfo), reinterpret_cast<float*>(ws + w.diag), desc->sigma,
-          reinterpret_cast<int*>(ws + w.selcol), reinterpret_cast<float*>(ws + w.selL2), rowstat, rowloss);
+          reinterpret_cast<int*>(ws + w.selcol), reinterpret_cast<float*>(ws + w.selL2), rowstat, rowloss, hard);
       XB_LAUNCHED();
     }
   } else {

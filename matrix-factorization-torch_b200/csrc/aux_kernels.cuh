@@ -996,7 +996,7 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
                                      const float4* __restrict__ qfwd, const float2* __restrict__ ipar,
                                      const float4* __restrict__ rowinfo, const float* __restrict__ diag,
                                      float sigma, int* __restrict__ selcol, float* __restrict__ selL2,
-                                     float4* __restrict__ rowstat, float* __restrict__ rowloss) {
+                                     float4* __restrict__ rowstat, float* __restrict__ rowloss, bool hard) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -1041,6 +1041,10 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
     double r = a2d * (dii - dij) - (lq2j - lq2i);
     r += 0.0;  // -0 -> +0 (hard side, losses.py:149 tests `< 0`)
     unsigned long long key = static_cast<unsigned long long>(__double_as_longlong(r)) ^ 0x7fffffffffffffffull;
+    if (hard) {   // hard_mining (losses.py:112-132): the K largest logits, i.e. R descending
+      const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(r));
+      key = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
     key = (r != r) ? 1ull : (key < 1ull ? 1ull : key);
     const float l2 = static_cast<float>(-a2d * dij - lq2j);
     if ((s & 31) == lane) {

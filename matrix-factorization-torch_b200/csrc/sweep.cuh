@@ -118,7 +118,7 @@ struct SweepParams {
   long long* trace;          // debug: [tiles][8] clock64 stamps from CTA (0,0) (producer, MMA issuer, epilogue warp 2)
   int trace_tiles;           // number of tiles traced (from tile 0 of the CTA)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
-                             // 2: same with R negated (hard side first)
+                             // 2: same with R negated (hard side first)   3: key = order(R) (hard mining, losses.py:112-132)
   // GRAD, item-major sweep of an exponential loss (see grad_fold_kernel): the column operand is the sign-folded
   // query tile and its aug block carries the per-query offset, so x_ij = cabs * T_ij - lq2_i and |G_ij| = 2^x_ij
   float cabs;                // |sigma| * log2(e)
@@ -1146,6 +1146,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 r += 0.0f;                                     // -0 -> +0 (losses.py:149 tests `< 0`)
               }
               uint32_t kk = __float_as_uint(r) ^ 0x7fffffffu;
+              if (p.topk_mining == 3) kk = order_key(r);       // hard mining: R descending (= logit descending)
               kk = (r != r) ? 1u : max(kk, 1u);
               w[c] = kk;
               kmax = max(kmax, kk);

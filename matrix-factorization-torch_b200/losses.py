@@ -50,6 +50,7 @@ def _make_desc(
     sigma: float,
     margin: float,
     has_log_q: bool,
+    mining: int = 0,
 ) -> _lib.LossDesc:
     return _lib.LossDesc(
         batch=batch,
@@ -63,7 +64,7 @@ def _make_desc(
         sigma=sigma,
         margin=margin,
         has_log_q=int(has_log_q),
-        reserved=0,
+        mining=mining,
     )
 
 
@@ -87,6 +88,7 @@ def _loss_fwd(
     margin: float,
     loss_mask: int,
     compute: int,
+    mining: int,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     device = _lib.require_cuda(user_embed, item_embed, target, item_idx, pos_idx, log_q)
     desc = _make_desc(
@@ -101,6 +103,7 @@ def _loss_fwd(
         sigma,
         margin,
         log_q is not None,
+        mining,
     )
     ws_bytes = _workspace_bytes(desc)
     with torch.cuda.device(device):
@@ -124,7 +127,7 @@ def _loss_fwd(
 
 
 @_loss_fwd.register_fake
-def _(user_embed, item_embed, target, item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute):  # noqa: ANN001, ANN202, PLR0913
+def _(user_embed, item_embed, target, item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute, mining):  # noqa: ANN001, ANN202, PLR0913
     desc = _make_desc(
         user_embed.size(0),
         item_embed.size(0),
@@ -137,6 +140,7 @@ def _(user_embed, item_embed, target, item_idx, pos_idx, log_q, num_negatives, s
         sigma,
         margin,
         log_q is not None,
+        mining,
     )
     return (
         user_embed.new_empty(_lib.XB_NUM_LOSSES, dtype=torch.float32),
@@ -159,11 +163,13 @@ def _loss_bwd(
     margin: float,
     loss_mask: int,
     compute: int,
+    mining: int,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     device = _lib.require_cuda(workspace, d_losses)
     dtype = torch.bfloat16 if bf16_io else torch.float32
     desc = _make_desc(
-        batch, num_items, dim, num_pos, _lib.dtype_code(dtype), compute, num_negatives, loss_mask, sigma, margin, has_log_q
+        batch, num_items, dim, num_pos, _lib.dtype_code(dtype), compute, num_negatives, loss_mask, sigma, margin, has_log_q,
+        mining,
     )
     with torch.cuda.device(device):
         d_user = torch.empty(batch, dim, dtype=dtype, device=device)
@@ -182,13 +188,13 @@ def _loss_bwd(
 
 
 @_loss_bwd.register_fake
-def _(workspace, d_losses, batch, num_items, dim, num_pos, bf16_io, has_log_q, num_negatives, sigma, margin, loss_mask, compute):  # noqa: ANN001, ANN202, PLR0913
+def _(workspace, d_losses, batch, num_items, dim, num_pos, bf16_io, has_log_q, num_negatives, sigma, margin, loss_mask, compute, mining):  # noqa: ANN001, ANN202, PLR0913
     dtype = torch.bfloat16 if bf16_io else torch.float32
     return workspace.new_empty(batch, dim, dtype=dtype), workspace.new_empty(num_items, dim, dtype=dtype)
 
 
 def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
-    user_embed, item_embed, _target, _item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute = inputs
+    user_embed, item_embed, _target, _item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute, mining = inputs
     _losses, workspace = output
     import os  # noqa: PLC0415
     if os.environ.get("XB_AB", "1") == "1":
@@ -207,15 +213,16 @@ def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
         margin,
         loss_mask,
         compute,
+        mining,
     )
 
 
 def _backward(ctx, d_losses, _d_workspace):  # noqa: ANN001, ANN202
     (workspace,) = ctx.saved_tensors
     if d_losses is None:
-        return (None,) * 11
+        return (None,) * 12
     d_user, d_item = _loss_bwd(workspace, d_losses.contiguous().float(), *ctx.meta)
-    return d_user, d_item, None, None, None, None, None, None, None, None, None
+    return d_user, d_item, None, None, None, None, None, None, None, None, None, None
 
 
 _loss_fwd.register_autograd(_backward, setup_context=_setup_context)
@@ -250,10 +257,13 @@ def fused_losses(
     margin: float = 1.0,
     loss_mask: int = ALL_LOSSES,
     compute: str | None = None,
+    mining: str = "semi_hard",
 ) -> torch.Tensor:
     """All selected losses in one contraction: returns a float32 vector of 7 slots (``LOSS_SLOTS``).
 
-    Unselected slots are 0.  Differentiable w.r.t. ``user_embed`` and ``item_embed``.
+    Unselected slots are 0.  Differentiable w.r.t. ``user_embed`` and ``item_embed``.  ``mining`` picks which
+    ``num_negatives`` columns survive: ``"semi_hard"`` (``semi_hard_mining``, losses.py:134-162 — what every
+    reference loss calls) or ``"hard"`` (``hard_mining``, losses.py:112-132, defined but never called there).
     """
     check_inputs(user_embed, item_embed, target)
     device = _lib.require_cuda(user_embed, item_embed, target, item_idx, pos_idx, log_q)
@@ -288,6 +298,7 @@ def fused_losses(
         float(margin),
         int(loss_mask),
         _lib.compute_code(compute, user_embed.dtype),
+        _lib.mining_code(mining),
     )
     return losses
 
@@ -302,12 +313,15 @@ class EmbeddingLoss(torch.nn.Module, abc.ABC):
         sigma: float = 1.0,
         margin: float = 1.0,
         compute: str | None = None,
+        mining: str = "semi_hard",
     ) -> None:
         super().__init__()
         self.num_negatives = num_negatives
         self.sigma = sigma
         self.margin = margin
         self.compute = compute
+        _lib.mining_code(mining)  # validates
+        self.mining = mining
 
     @property
     def slot(self) -> int:
@@ -351,6 +365,7 @@ class EmbeddingLoss(torch.nn.Module, abc.ABC):
             margin=self.margin,
             loss_mask=1 << self.slot,
             compute=self.compute,
+            mining=self.mining,
         )
         return losses[self.slot]
 

@@ -44,13 +44,19 @@ CASES = [
     ("square_no_negs", 32, 32, 32, 3, 200, 0, 1.0, 1.0, False, True, 1.0),
     ("ragged_tile", 130, 300, 48, 6, 150, 0, 4.0, -0.5, True, True, 1.0),
     ("mined_k16_ragged", 130, 300, 48, 6, 150, 16, 4.0, 0.25, False, True, 1.0),
+    # names starting with "hard": the reference's own (never-called) hard_mining method (losses.py:112-132) is bound in
+    # place of semi_hard_mining on each module instance; the classes themselves stay unmodified
+    ("hard_k4", 48, 112, 32, 5, 60, 4, 1.0, 1.0, False, True, 1.0),
+    ("hard_k16_ragged_signed", 130, 300, 48, 6, 150, 16, 4.0, 0.25, True, True, 1.0),
 ]
 
 
-def run_reference(inp: dict[str, torch.Tensor], k: int, sigma: float, margin: float, dtype: torch.dtype):
+def run_reference(inp: dict[str, torch.Tensor], k: int, sigma: float, margin: float, dtype: torch.dtype, hard: bool = False):
     out = {}
     for name in NAMES:
         module = getattr(ref, name)(num_negatives=k, sigma=sigma, margin=margin)
+        if hard:
+            module.semi_hard_mining = module.hard_mining
         q = inp["user_embed"].to(dtype).clone().requires_grad_(True)
         v = inp["item_embed"].to(dtype).clone().requires_grad_(True)
         loss = module(q, v, inp["target"].to(dtype), item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
@@ -64,21 +70,24 @@ def run_reference(inp: dict[str, torch.Tensor], k: int, sigma: float, margin: fl
     return out
 
 
-def main() -> None:
+def main(only: set[str] | None = None) -> None:
     for i, (name, b, n, d, p, ncat, k, sigma, margin, signed, normalize, scale) in enumerate(CASES):
         inp = synthetic.make_loss_inputs(
             b, n, d, p, n_catalog=ncat, seed=1000 + i, signed_targets=signed, normalize=normalize, scale=scale,
             mean_extra_pos=2.0,
         )
-        r64 = run_reference(inp, k, sigma, margin, torch.float64)
-        r32 = run_reference(inp, k, sigma, margin, torch.float32)
+        if only is not None and name not in only:
+            continue
+        hard = name.startswith("hard")
+        r64 = run_reference(inp, k, sigma, margin, torch.float64, hard)
+        r32 = run_reference(inp, k, sigma, margin, torch.float32, hard)
         arrays = {
             "user_embed": inp["user_embed"].numpy(),
             "item_embed": inp["item_embed"].numpy(),
             "target": inp["target"].numpy(),
             "item_idx": inp["item_idx"].numpy(),
             "pos_idx": inp["pos_idx"].numpy(),
-            "config": np.array([k, sigma, margin], dtype=np.float64),
+            "config": np.array([k, sigma, margin, 1.0 if hard else 0.0], dtype=np.float64),
             "torch_version": np.array(torch.__version__),
         }
         for lname in NAMES:
@@ -91,4 +100,4 @@ def main() -> None:
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]) or None)   # optional: case names to (re)generate; the committed files of the others stay

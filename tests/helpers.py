@@ -25,7 +25,8 @@ def golden_cases() -> list[str]:
 
 def load_golden(name: str) -> dict:
     z = np.load(GOLDEN_DIR / f"{name}.npz")
-    k, sigma, margin = z["config"]
+    k, sigma, margin = z["config"][:3]
+    mining = "hard" if len(z["config"]) > 3 and z["config"][3] else "semi_hard"  # noqa: PLR2004
     case = {
         "user_embed": torch.from_numpy(z["user_embed"]),
         "item_embed": torch.from_numpy(z["item_embed"]),
@@ -35,6 +36,7 @@ def load_golden(name: str) -> dict:
         "num_negatives": int(k),
         "sigma": float(sigma),
         "margin": float(margin),
+        "mining": mining,
         "expected": {},
     }
     for n in LOSS_NAMES:

@@ -63,13 +63,13 @@ def test_workspace_queries_need_no_gpu() -> None:
     from xfmr_b200 import _lib  # noqa: PLC0415
 
     desc = _lib.LossDesc(batch=4096, num_items=87585, dim=128, num_pos=32, in_dtype=1, compute=0, num_negatives=0,
-                         loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, reserved=0)
+                         loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, mining=0)
     assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(desc)) > 0
     bad = _lib.LossDesc(batch=8, num_items=4, dim=128, num_pos=0, in_dtype=1, compute=0, num_negatives=0,
-                        loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, reserved=0)
+                        loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, mining=0)
     assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(bad)) == 0
     assert b"batch" in _lib.lib.xb_last_error_string()
     too_wide = _lib.LossDesc(batch=8, num_items=16, dim=512, num_pos=0, in_dtype=1, compute=0, num_negatives=0,
-                             loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, reserved=0)
+                             loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, mining=0)
     assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(too_wide)) == 0
     assert xfmr_b200._lib.lib.xb_mask_words(3706) == 4 * 29  # noqa: SLF001

@@ -18,13 +18,14 @@ RTOL = 1e-3
 
 
 def cuda_losses_and_grads(inp: dict, *, num_negatives: int, sigma: float, margin: float, dtype=torch.float32,
-                          compute=None, log_q=None, names=LOSS_NAMES) -> dict:
+                          compute=None, log_q=None, names=LOSS_NAMES, mining="semi_hard") -> dict:
     import xfmr_b200  # noqa: PLC0415
 
     dev = torch.device("cuda:0")
     out = {}
     for n in names:
-        module = getattr(xfmr_b200, n)(num_negatives=num_negatives, sigma=sigma, margin=margin, compute=compute)
+        module = getattr(xfmr_b200, n)(num_negatives=num_negatives, sigma=sigma, margin=margin, compute=compute,
+                                       mining=mining)
         q = inp["user_embed"].to(dev, dtype).requires_grad_(True)
         v = inp["item_embed"].to(dev, dtype).requires_grad_(True)
         loss = module(q, v, inp["target"].to(dev), item_idx=inp["item_idx"].to(dev), pos_idx=inp["pos_idx"].to(dev),
@@ -40,7 +41,7 @@ def cuda_losses_and_grads(inp: dict, *, num_negatives: int, sigma: float, margin
 
 
 def oracle_losses_and_grads(inp: dict, *, num_negatives: int, sigma: float, margin: float, round_bf16=False,
-                            log_q=None, device="cpu", names=LOSS_NAMES) -> dict:
+                            log_q=None, device="cpu", names=LOSS_NAMES, mining="semi_hard") -> dict:
     from oracle import losses_oracle  # noqa: PLC0415
 
     q, v = inp["user_embed"], inp["item_embed"]
@@ -50,6 +51,7 @@ def oracle_losses_and_grads(inp: dict, *, num_negatives: int, sigma: float, marg
         q.to(device).double(), v.to(device).double(), inp["target"].to(device).double(),
         item_idx=inp["item_idx"].to(device), pos_idx=inp["pos_idx"].to(device), num_negatives=num_negatives,
         sigma=sigma, margin=margin, log_q=None if log_q is None else log_q.to(device).double(), names=names,
+        mining=mining,
     )
 
 
@@ -71,7 +73,8 @@ def assert_close(got: dict, ref: dict, rtol: float = RTOL, label: str = "") -> N
 @pytest.mark.parametrize("name", golden_cases())
 def test_reference_golden_fp32(name: str) -> None:
     case = load_golden(name)
-    got = cuda_losses_and_grads(case, num_negatives=case["num_negatives"], sigma=case["sigma"], margin=case["margin"])
+    got = cuda_losses_and_grads(case, num_negatives=case["num_negatives"], sigma=case["sigma"], margin=case["margin"],
+                                mining=case["mining"])
     assert_close(got, case["expected"], label=name)
 
 
@@ -273,3 +276,22 @@ def test_graphed_step_matches_eager_and_takes_host_inputs() -> None:
     # device inputs go through the same path
     res = stepper.submit({k: batches[1][k].to(dev) for k in keys})
     assert res.loss_value() == pytest.approx(results[1][0], rel=1e-6)
+
+
+@pytest.mark.parametrize(("k", "dtype"), [(4, torch.float32), (32, torch.float32), (8, torch.bfloat16)])
+def test_hard_mining_larger_shapes(k: int, dtype: torch.dtype) -> None:
+    """``mining="hard"`` (``hard_mining``, losses.py:112-132) on shapes with several row blocks and column chunks."""
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    inp = synthetic.make_loss_inputs(700, 5000, 64, 6, n_catalog=3000, seed=40 + k, signed_targets=True, mean_extra_pos=2.0)
+    bf16 = dtype == torch.bfloat16
+    got = cuda_losses_and_grads(inp, num_negatives=k, sigma=3.0, margin=0.4, dtype=dtype, mining="hard")
+    ref = oracle_losses_and_grads(inp, num_negatives=k, sigma=3.0, margin=0.4, round_bf16=bf16, mining="hard")
+    assert_close(got, ref, rtol=2.0**-7 if bf16 else RTOL, label=f"hard k={k}")
+
+
+def test_mining_keyword_is_validated() -> None:
+    import xfmr_b200  # noqa: PLC0415
+
+    with pytest.raises(ValueError, match="mining"):
+        xfmr_b200.PairwiseHingeLoss(num_negatives=4, mining="easy")

@@ -59,11 +59,14 @@ def test_fake_tensor_shapes() -> None:
         t = torch.empty(64, device="cuda")
         idx = torch.empty(200, dtype=torch.int64, device="cuda")
         pos = torch.empty(64, 4, dtype=torch.int64, device="cuda")
-        losses, ws = torch.ops.xfmr_b200.loss_fwd(q, v, t, idx, pos, None, 0, 1.0, 1.0, 127, 1)
+        losses, ws = torch.ops.xfmr_b200.loss_fwd(q, v, t, idx, pos, None, 0, 1.0, 1.0, 127, 1, 0)
         assert losses.shape == (7,) and losses.dtype == torch.float32
         assert ws.dtype == torch.uint8 and ws.numel() > 0
-        dq, dv = torch.ops.xfmr_b200.loss_bwd(ws, losses, 64, 200, 32, 4, False, False, 0, 1.0, 1.0, 127, 1)
+        dq, dv = torch.ops.xfmr_b200.loss_bwd(ws, losses, 64, 200, 32, 4, False, False, 0, 1.0, 1.0, 127, 1, 0)
         assert dq.shape == (64, 32) and dv.shape == (200, 32)
+        loss, ws_u = torch.ops.xfmr_b200.uniformity_fwd(q, 2.0, 1)
+        assert loss.shape == (1,) and ws_u.numel() > ws.numel() // 4
+        assert torch.ops.xfmr_b200.uniformity_bwd(ws_u, loss, 64, 32, False, 2.0, 1).shape == (64, 32)
 
 
 def test_unsupported_shapes_are_reported_by_the_library() -> None:
@@ -77,7 +80,7 @@ def test_unsupported_shapes_are_reported_by_the_library() -> None:
     big_k = _lib.TopkDesc(num_queries=4, num_items=100, dim=64, k=1000, in_dtype=0, compute=0, has_exclusions=0, reserved=0, id_base=0)
     assert _lib.lib.xb_topk_workspace_bytes(ctypes.byref(big_k)) == 0
     mined = _lib.LossDesc(batch=8, num_items=1000, dim=64, num_pos=0, in_dtype=0, compute=1, num_negatives=100,
-                          loss_mask=8, sigma=1.0, margin=1.0, has_log_q=0, reserved=0)
+                          loss_mask=8, sigma=1.0, margin=1.0, has_log_q=0, mining=0)
     assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(mined)) == 0
 
 

@@ -23,7 +23,7 @@ def test_oracle_matches_reference_golden(name: str) -> None:
     got = losses_oracle.losses_and_grads(
         case["user_embed"].double(), case["item_embed"].double(), case["target"].double(),
         item_idx=case["item_idx"], pos_idx=case["pos_idx"], num_negatives=case["num_negatives"],
-        sigma=case["sigma"], margin=case["margin"],
+        sigma=case["sigma"], margin=case["margin"], mining=case["mining"],
     )
     for n in LOSS_NAMES:
         loss, dq, dv = got[n]
