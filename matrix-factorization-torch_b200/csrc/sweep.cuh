@@ -880,6 +880,35 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     int cnt = 0;
     uint32_t thr = row_ok ? 0u : 0xffffffffu;       // mining: entries with key <= thr can no longer enter the top `keep`
     float thr_f = row_ok ? -INFINITY : INFINITY;    // retrieval: scores below thr_f can no longer enter
+    // Mining: the keys above `thr` are a window of R = L_ij - L_ii.  Semi-hard order (keys of R < 0 rank above all
+    // R >= 0, closest to 0 first): once the keep-th best is semi-hard, rt = R(thr) < 0 and the window is [rt, 0]
+    // (mode 2, mirrored: [0, -rt]); before that every column may enter (`wopen`).  Hard order (mode 3): R >= rt.
+    // The vote tests u = a2 * S + wb against whalf (|u| <= whalf, mode 3: u >= -whalf); wb / whalf carry a rounding
+    // slack, the exact key comparison is made on the append path.
+    float wb = 0.f, whalf = -1.f;
+    bool wopen = false;
+    auto set_window = [&]() {
+      const float c0 = rp_reg[2];
+      wopen = false;
+      wb = c0;
+      whalf = -1.f;
+      if (thr == 0xffffffffu) {                     // dead row: nothing enters
+        if (p.topk_mining == 3) wb = -INFINITY;
+        return;
+      }
+      if (p.topk_mining == 3) {
+        const float rt = order_key_inv(thr);
+        if (thr == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }
+        whalf = 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
+        wb = c0 - rt;
+      } else {
+        const float rt = __uint_as_float(thr ^ 0x7fffffffu);
+        if ((thr & 0x80000000u) == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }
+        whalf = -0.5f * rt + 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
+        wb = c0 - ((p.topk_mining == 2) ? -0.5f * rt : 0.5f * rt);
+      }
+    };
+    if (MODE == MODE_TOPK && LM != 0) set_window();
 
     // Per-tile side inputs (mask words of this row, parameters of the tile's columns) come from global
     // memory; they are fetched ONE TILE AHEAD into registers so their latency hides behind the tile math.
@@ -1110,76 +1139,15 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           }
           tmem_st8(buf_addr + static_cast<uint32_t>(k * UW), pk);
         } else if constexpr (MODE == MODE_TOPK) {
-          // Streaming selection.  Fast path: one 3-input max per two elements against the row's threshold and one warp
-          // vote; a unit in which some row can beat its current k-th best takes the append path below.
+          // Streaming selection.  Fast path: a cheap float test of the unit against the row's admission threshold and
+          // one warp vote; a unit in which some row can beat its current k-th best takes the append path below.
           constexpr bool MINING = LM != 0;
-          uint32_t w[16];     // words staged for the scan: raw score bits (retrieval) or keys (mining)
-          bool hit;
-          if (!MINING) {
-            float m0 = fmaxf(__uint_as_float(s[0]), fmaxf(__uint_as_float(s[1]), __uint_as_float(s[2])));
-            float m1 = fmaxf(__uint_as_float(s[3]), fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5])));
-            float m2 = fmaxf(__uint_as_float(s[6]), fmaxf(__uint_as_float(s[7]), __uint_as_float(s[8])));
-            float m3 = fmaxf(__uint_as_float(s[9]), fmaxf(__uint_as_float(s[10]), __uint_as_float(s[11])));
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[12]), __uint_as_float(s[13])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[14]), __uint_as_float(s[15])));
-            hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) w[c] = s[c];
-          } else {
-            // mining: key = bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by R asc);
-            // mode 2 mirrors the order (see mined_forward_kernel)
-            uint32_t kmax = 0;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float S = __uint_as_float(s[c]);
-              // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
-              //  per-tile barrier, so a compacting warp never stalls the others)
-              float l2 = rp_reg[0] * S;                         // norms ride in the contraction
-              if (LOGQ) {
-                const int jc = min(j0 + ucol + c, p.nC - 1);
-                l2 -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
-              }
-              float r = l2 + rp_reg[2];                        // rp_reg[2] = -L2_ii: R = L_ij - L_ii
-              if (p.topk_mining == 2) {
-                r = (r == 0.f) ? -0.0f : -r;                   // mirrored order; an exact 0 belongs to BOTH first groups
-              } else {
-                r += 0.0f;                                     // -0 -> +0 (losses.py:149 tests `< 0`)
-              }
-              uint32_t kk = __float_as_uint(r) ^ 0x7fffffffu;
-              if (p.topk_mining == 3) kk = order_key(r);       // hard mining: R descending (= logit descending)
-              kk = (r != r) ? 1u : max(kk, 1u);
-              w[c] = kk;
-              kmax = max(kmax, kk);
-            }
-            hit = kmax > thr;
-          }
-          uint32_t hm = __ballot_sync(0xffffffffu, hit);
-          if (hm) {
-            // Every lane parks its 16 words in shared memory (dynamic indexing), builds the bit mask of its passing
-            // columns and appends them to its OWN row's buffer: no shuffles, and the cost does not grow with the number
-            // of rows that hit (the mining sweeps and the start of a retrieval sweep hit in nearly every unit).
-            uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(mine + q4 * 4) = make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
-            uint32_t pm = 0u;
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-              pm |= (MINING ? (w[c] > thr) : (__uint_as_float(w[c]) >= thr_f)) ? (1u << c) : 0u;
-            pm &= ~mu;
-            unsigned long long* cb = p.cand + out_row * p.cap;
-            const uint32_t col0 = static_cast<uint32_t>(j0 + ucol);
-            while (pm) {
-              const int c = __ffs(pm) - 1;
-              pm &= pm - 1;
-              const uint32_t x = mine[c];
-              const uint32_t key = MINING ? x : max(order_key(__uint_as_float(x)), 1u);
-              cb[cnt++] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
-            }
-            __syncwarp();
-            // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
-            // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
-            // column wins ties).
+          unsigned long long* cb = p.cand + out_row * p.cap;
+          const uint32_t col0 = static_cast<uint32_t>(j0 + ucol);
+          // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
+          // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
+          // column wins ties).
+          auto compact_full_rows = [&]() {
             uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
             while (need) {
               const int src = __ffs(need) - 1;
@@ -1194,7 +1162,104 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 const uint32_t kk = static_cast<uint32_t>(kth >> 32);
                 thr = kk > 0 ? kk - 1 : 0;
                 thr_f = order_key_inv(kk);
+                if (MINING) set_window();
               }
+            }
+          };
+          if constexpr (!MINING) {
+            float m0 = fmaxf(__uint_as_float(s[0]), fmaxf(__uint_as_float(s[1]), __uint_as_float(s[2])));
+            float m1 = fmaxf(__uint_as_float(s[3]), fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5])));
+            float m2 = fmaxf(__uint_as_float(s[6]), fmaxf(__uint_as_float(s[7]), __uint_as_float(s[8])));
+            float m3 = fmaxf(__uint_as_float(s[9]), fmaxf(__uint_as_float(s[10]), __uint_as_float(s[11])));
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[12]), __uint_as_float(s[13])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[14]), __uint_as_float(s[15])));
+            const bool hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
+            if (__ballot_sync(0xffffffffu, hit)) {
+              // Every lane parks its 16 words in shared memory (dynamic indexing), builds the bit mask of its passing
+              // columns and appends them to its OWN row's buffer: no shuffles, and the cost does not grow with the
+              // number of rows that hit (the start of a retrieval sweep hits in nearly every unit).
+              uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                *reinterpret_cast<uint4*>(mine + q4 * 4) = make_uint4(s[4 * q4], s[4 * q4 + 1], s[4 * q4 + 2], s[4 * q4 + 3]);
+              uint32_t pm = 0u;
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pm |= (__uint_as_float(s[c]) >= thr_f) ? (1u << c) : 0u;
+              pm &= ~mu;
+              while (pm) {
+                const int c = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t key = max(order_key(__uint_as_float(mine[c])), 1u);
+                cb[cnt++] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+              }
+              __syncwarp();
+              compact_full_rows();
+            }
+          } else {
+            // Mining.  The exact key is bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by
+            // R asc; mode 2 mirrors the order, mode 3 = hard mining orders by R desc).  Keys above the threshold form a
+            // WINDOW of R (see set_window), so the vote needs one FMA per element, u = R - window centre, and a min
+            // tree over |u| (mode 3: a max tree over u); the window is conservative, the exact key decides below.
+            float u[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              u[c] = fmaf(rp_reg[0], __uint_as_float(s[c]), wb);
+              if (LOGQ) {
+                // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
+                //  per-tile barrier, so a compacting warp never stalls the others)
+                const int jc = min(j0 + ucol + c, p.nC - 1);
+                u[c] -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+              }
+            }
+            const bool hard_order = p.topk_mining == 3;
+            bool hit;
+            if (hard_order) {
+              float m0 = fmaxf(u[0], fmaxf(u[1], u[2])), m1 = fmaxf(u[3], fmaxf(u[4], u[5]));
+              float m2 = fmaxf(u[6], fmaxf(u[7], u[8])), m3 = fmaxf(u[9], fmaxf(u[10], u[11]));
+              m0 = fmaxf(m0, fmaxf(u[12], u[13]));
+              m1 = fmaxf(m1, fmaxf(u[14], u[15]));
+              hit = wopen || fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= -whalf;
+            } else {
+              float m0 = fminf(fabsf(u[0]), fminf(fabsf(u[1]), fabsf(u[2]))), m1 = fminf(fabsf(u[3]), fminf(fabsf(u[4]), fabsf(u[5])));
+              float m2 = fminf(fabsf(u[6]), fminf(fabsf(u[7]), fabsf(u[8]))), m3 = fminf(fabsf(u[9]), fminf(fabsf(u[10]), fabsf(u[11])));
+              m0 = fminf(m0, fminf(fabsf(u[12]), fabsf(u[13])));
+              m1 = fminf(m1, fminf(fabsf(u[14]), fabsf(u[15])));
+              hit = wopen || fminf(fminf(m0, m1), fminf(m2, m3)) <= whalf;
+            }
+            if (__ballot_sync(0xffffffffu, hit)) {
+              uint32_t pm = 0u;
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                pm |= (wopen || (hard_order ? (u[c] >= -whalf) : (fabsf(u[c]) <= whalf))) ? (1u << c) : 0u;
+              pm &= ~mu;
+              if (pm) {
+                // only lanes with a candidate park their 16 raw scores (dynamic indexing) and evaluate exact keys
+                uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  *reinterpret_cast<uint4*>(mine + q4 * 4) = make_uint4(s[4 * q4], s[4 * q4 + 1], s[4 * q4 + 2], s[4 * q4 + 3]);
+                while (pm) {
+                  const int c = __ffs(pm) - 1;
+                  pm &= pm - 1;
+                  float l2 = rp_reg[0] * __uint_as_float(mine[c]);   // norms ride in the contraction
+                  if (LOGQ) {
+                    const int jc = min(j0 + ucol + c, p.nC - 1);
+                    l2 -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+                  }
+                  float r = l2 + rp_reg[2];                          // rp_reg[2] = -L2_ii: R = L_ij - L_ii
+                  if (p.topk_mining == 2) {
+                    r = (r == 0.f) ? -0.0f : -r;                     // mirrored order; an exact 0 belongs to BOTH first groups
+                  } else {
+                    r += 0.0f;                                       // -0 -> +0 (losses.py:149 tests `< 0`)
+                  }
+                  uint32_t kk = hard_order ? order_key(r) : (__float_as_uint(r) ^ 0x7fffffffu);
+                  kk = (r != r) ? 1u : max(kk, 1u);
+                  if (kk > thr)
+                    cb[cnt++] = (static_cast<unsigned long long>(kk) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+                }
+              }
+              __syncwarp();
+              compact_full_rows();
             }
           }
         }
