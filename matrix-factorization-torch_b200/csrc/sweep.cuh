@@ -452,8 +452,12 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long (&e)[PER_LANE]
 // bit-wise binary search (64 rounds of "how many entries are >= candidate", counted across the warp); this is
 // ~10x less code and work than sorting the buffer, which matters because the compaction sits inside the
 // sweep's epilogue.  Returns the keep-th largest entry (the new admission threshold).
+// `slack` > 0 lets the search stop as soon as between keep and keep + slack entries lie at or above the candidate
+// (typically after half of the 32 rounds): a few more entries survive and the threshold is a little looser, both
+// harmless for a streaming selection; `*kept` receives the number of surviving entries.  slack = 0 is exact.
 template <int PER_LANE>
-__device__ __forceinline__ unsigned long long compact_select(unsigned long long* buf, int cnt, int keep, int lane) {
+__device__ __forceinline__ unsigned long long compact_select(unsigned long long* buf, int cnt, int keep, int lane,
+                                                             int slack = 0, int* kept = nullptr) {
   unsigned long long e[PER_LANE];
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) {
@@ -471,7 +475,10 @@ __device__ __forceinline__ unsigned long long compact_select(unsigned long long*
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) c += (static_cast<uint32_t>(e[i] >> 32) >= cand) ? 1 : 0;
     c = warp_total(c);
-    if (c >= keep) T = cand;
+    if (c >= keep) {
+      T = cand;
+      if (c <= keep + slack) break;   // (warp-uniform)
+    }
   }
   {
     int c = 0;
@@ -480,7 +487,8 @@ __device__ __forceinline__ unsigned long long compact_select(unsigned long long*
     c_ge = warp_total(c);
   }
   unsigned long long thr = static_cast<unsigned long long>(T) << 32;
-  if (c_ge > keep) {
+  if (kept != nullptr) *kept = c_ge > keep + slack ? keep : c_ge;
+  if (c_ge > keep + slack) {
     // ties on the key at the boundary: resolve on the low word (larger = lower column) among key == T
     int c_gt = 0;
 #pragma unroll
@@ -499,7 +507,7 @@ __device__ __forceinline__ unsigned long long compact_select(unsigned long long*
     }
     thr |= Lw;
   }
-  // entries >= thr are exactly the `keep` largest (entries are unique); compact them to the front
+  // entries >= thr are exactly the `keep` (up to keep + slack) largest (entries are unique); compact them to the front
   int mine = 0;
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) mine += (e[i] >= thr && e[i] != 0ull) ? 1 : 0;
@@ -518,13 +526,14 @@ __device__ __forceinline__ unsigned long long compact_select(unsigned long long*
   return thr;
 }
 
-static __device__ __noinline__ unsigned long long compact_dispatch(unsigned long long* buf, int cnt, int cap, int keep, int lane) {
+static __device__ __noinline__ unsigned long long compact_dispatch(unsigned long long* buf, int cnt, int cap, int keep, int lane,
+                                                                   int slack, int* kept) {
   switch (cap) {
-    case 64: return compact_select<2>(buf, cnt, keep, lane);
-    case 128: return compact_select<4>(buf, cnt, keep, lane);
-    case 256: return compact_select<8>(buf, cnt, keep, lane);
-    case 512: return compact_select<16>(buf, cnt, keep, lane);
-    default: return compact_select<32>(buf, cnt, keep, lane);
+    case 64: return compact_select<2>(buf, cnt, keep, lane, slack, kept);
+    case 128: return compact_select<4>(buf, cnt, keep, lane, slack, kept);
+    case 256: return compact_select<8>(buf, cnt, keep, lane, slack, kept);
+    case 512: return compact_select<16>(buf, cnt, keep, lane, slack, kept);
+    default: return compact_select<32>(buf, cnt, keep, lane, slack, kept);
   }
 }
 
@@ -880,32 +889,42 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     int cnt = 0;
     uint32_t thr = row_ok ? 0u : 0xffffffffu;       // mining: entries with key <= thr can no longer enter the top `keep`
     float thr_f = row_ok ? -INFINITY : INFINITY;    // retrieval: scores below thr_f can no longer enter
-    // Mining: the keys above `thr` are a window of R = L_ij - L_ii.  Semi-hard order (keys of R < 0 rank above all
-    // R >= 0, closest to 0 first): once the keep-th best is semi-hard, rt = R(thr) < 0 and the window is [rt, 0]
-    // (mode 2, mirrored: [0, -rt]); before that every column may enter (`wopen`).  Hard order (mode 3): R >= rt.
-    // The vote tests u = a2 * S + wb against whalf (|u| <= whalf, mode 3: u >= -whalf); wb / whalf carry a rounding
-    // slack, the exact key comparison is made on the append path.
-    float wb = 0.f, whalf = -1.f;
-    bool wopen = false;
+    // Mining: the keys above `thr` are a window of R = L_ij - L_ii (keys of R < 0 rank above all R >= 0, closest to
+    // 0 first).  With rt = R(thr):
+    //   semi-hard order, keep-th best semi-hard (rt < 0):   R in [rt, 0]        (mode 2, mirrored: [0, -rt])
+    //   semi-hard order, keep-th best still hard (rt >= 0): R <= rt             (mode 2: R >= -rt)
+    //   hard order (mode 3):                                R >= rt
+    // The vote evaluates u = wa * S + wb per element (wa = +-a2) and tests |u| <= whalf for a two-sided window,
+    // u <= whalf for a one-sided one (`wone`); whalf carries a rounding slack, the exact key decides on the append path.
+    float wa = rp_reg[0], wb = 0.f, whalf = -1.f;
+    bool wopen = false, wone = false;
     auto set_window = [&]() {
-      const float c0 = rp_reg[2];
+      const float a2 = rp_reg[0], c0 = rp_reg[2];
       wopen = false;
-      wb = c0;
+      wone = true;
+      wa = a2;
+      wb = 0.f;
       whalf = -1.f;
-      if (thr == 0xffffffffu) {                     // dead row: nothing enters
-        if (p.topk_mining == 3) wb = -INFINITY;
-        return;
-      }
-      if (p.topk_mining == 3) {
-        const float rt = order_key_inv(thr);
-        if (thr == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }
-        whalf = 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
+      if (thr == 0xffffffffu) { wb = INFINITY; return; }   // dead row: u = +inf (or NaN) never passes `u <= whalf`
+      const int mode = p.topk_mining;
+      const float rt = mode == 3 ? order_key_inv(thr) : __uint_as_float(thr ^ 0x7fffffffu);
+      if (thr == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }   // no threshold yet
+      const float slack = 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
+      if (mode == 3) {                              // R >= rt  <=>  -(R - rt) <= 0
+        wa = -a2;
+        wb = rt - c0;
+        whalf = slack;
+      } else if (thr & 0x80000000u) {               // two-sided: [rt, 0] or its mirror image [0, -rt]
+        wone = false;
+        wb = c0 - (mode == 2 ? -0.5f * rt : 0.5f * rt);
+        whalf = -0.5f * rt + slack;
+      } else if (mode == 2) {                       // -R <= rt
+        wa = -a2;
+        wb = -c0 - rt;
+        whalf = slack;
+      } else {                                      // R <= rt
         wb = c0 - rt;
-      } else {
-        const float rt = __uint_as_float(thr ^ 0x7fffffffu);
-        if ((thr & 0x80000000u) == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }
-        whalf = -0.5f * rt + 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
-        wb = c0 - ((p.topk_mining == 2) ? -0.5f * rt : 0.5f * rt);
+        whalf = slack;
       }
     };
     if (MODE == MODE_TOPK && LM != 0) set_window();
@@ -1155,10 +1174,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
               const int n = __shfl_sync(0xffffffffu, cnt, src);
               __syncwarp();
-              const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane);
+              int kept = p.keep;
+              // (a quarter more than `keep` may survive: the bit search then stops about half-way)
+              const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
               __syncwarp();
               if (lane == src) {
-                cnt = p.keep;
+                cnt = kept;
                 const uint32_t kk = static_cast<uint32_t>(kth >> 32);
                 thr = kk > 0 ? kk - 1 : 0;
                 thr_f = order_key_inv(kk);
@@ -1200,37 +1221,34 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             // R asc; mode 2 mirrors the order, mode 3 = hard mining orders by R desc).  Keys above the threshold form a
             // WINDOW of R (see set_window), so the vote needs one FMA per element, u = R - window centre, and a min
             // tree over |u| (mode 3: a max tree over u); the window is conservative, the exact key decides below.
-            float u[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              u[c] = fmaf(rp_reg[0], __uint_as_float(s[c]), wb);
+            auto uval = [&](int c) {
+              float x = fmaf(wa, __uint_as_float(s[c]), wb);
               if (LOGQ) {
                 // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
                 //  per-tile barrier, so a compacting warp never stalls the others)
                 const int jc = min(j0 + ucol + c, p.nC - 1);
-                u[c] -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+                const float lq = __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+                x -= (wa == rp_reg[0]) ? lq : -lq;
               }
-            }
+              return x;
+            };
             const bool hard_order = p.topk_mining == 3;
-            bool hit;
-            if (hard_order) {
-              float m0 = fmaxf(u[0], fmaxf(u[1], u[2])), m1 = fmaxf(u[3], fmaxf(u[4], u[5]));
-              float m2 = fmaxf(u[6], fmaxf(u[7], u[8])), m3 = fmaxf(u[9], fmaxf(u[10], u[11]));
-              m0 = fmaxf(m0, fmaxf(u[12], u[13]));
-              m1 = fmaxf(m1, fmaxf(u[14], u[15]));
-              hit = wopen || fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= -whalf;
-            } else {
-              float m0 = fminf(fabsf(u[0]), fminf(fabsf(u[1]), fabsf(u[2]))), m1 = fminf(fabsf(u[3]), fminf(fabsf(u[4]), fabsf(u[5])));
-              float m2 = fminf(fabsf(u[6]), fminf(fabsf(u[7]), fabsf(u[8]))), m3 = fminf(fabsf(u[9]), fminf(fabsf(u[10]), fabsf(u[11])));
-              m0 = fminf(m0, fminf(fabsf(u[12]), fabsf(u[13])));
-              m1 = fminf(m1, fminf(fabsf(u[14]), fabsf(u[15])));
-              hit = wopen || fminf(fminf(m0, m1), fminf(m2, m3)) <= whalf;
+            // two min trees: over |u| (two-sided windows) and over u (one-sided); NaN operands drop out of fminf
+            float a0 = INFINITY, o0 = INFINITY;
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              const float x = uval(c), y = uval(c + 1);
+              a0 = fminf(a0, fminf(fabsf(x), fabsf(y)));
+              o0 = fminf(o0, fminf(x, y));
             }
+            const bool hit = wopen || (wone ? o0 : a0) <= whalf;
             if (__ballot_sync(0xffffffffu, hit)) {
               uint32_t pm = 0u;
 #pragma unroll
-              for (int c = 0; c < 16; ++c)
-                pm |= (wopen || (hard_order ? (u[c] >= -whalf) : (fabsf(u[c]) <= whalf))) ? (1u << c) : 0u;
+              for (int c = 0; c < 16; ++c) {
+                const float x = uval(c);
+                pm |= (wopen || (wone ? x : fabsf(x)) <= whalf) ? (1u << c) : 0u;
+              }
               pm &= ~mu;
               if (pm) {
                 // only lanes with a candidate park their 16 raw scores (dynamic indexing) and evaluate exact keys
