@@ -34,6 +34,7 @@ from .retrieval import (
     METRIC_NAMES,
     TOP_K,
     ItemProcessor,
+    arrow_to_catalog,
     build_pair_mask,
     retrieval_metrics,
     topk_filter,
@@ -65,6 +66,7 @@ __all__ = [
     "StepResult",
     "UniformityLoss",
     "XbError",
+    "arrow_to_catalog",
     "build_pair_mask",
     "distributed",
     "fused_losses",

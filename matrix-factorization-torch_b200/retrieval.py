@@ -228,6 +228,40 @@ def pad_id_lists(lists: Sequence[Sequence[int]], *, pad: int = _PAD_ID, dtype: t
     return torch.tensor([list(e) + [pad] * (width - len(e)) for e in lists], dtype=dtype)
 
 
+ITEMS_PARQUET = "items.parquet"        # bundle files written by ItemProcessor.save
+PROCESSORS_JSON = "processors.json"    # same file name as the reference's export bundle (xfmr_rec/params.py)
+
+
+def arrow_to_catalog(table, *, id_col: str, text_col: str | None, embedding_col: str = "embedding"):  # noqa: ANN001, ANN201
+    """``(embeddings float32 [N, d] numpy, ids int64 numpy, texts list | None)`` from a pyarrow table with the schema
+    the reference writes into LanceDB: ``movie_rn, movie_id, movie_text, embedding: fixed_size_list<float32, d>``
+    (``ItemProcessor.get_index``, xfmr_rec/data/lightning.py:189, :208-219) — e.g. ``lance_table.to_arrow()`` or a parquet
+    copy of it.  Variable-length list columns are accepted when every row has the same length.
+    """
+    import numpy as np  # noqa: PLC0415
+    import pyarrow as pa  # noqa: PLC0415
+
+    col = table[embedding_col]
+    col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    num_rows = len(col)
+    if col.null_count:
+        msg = f"{col.null_count} rows have no embedding"
+        raise ValueError(msg)
+    flat = col.flatten().to_numpy(zero_copy_only=False)
+    if num_rows == 0 or flat.size % num_rows != 0:
+        msg = f"embedding column is ragged or empty: {flat.size} values in {num_rows} rows"
+        raise ValueError(msg)
+    if pa.types.is_list(col.type) or pa.types.is_large_list(col.type):
+        lengths = np.diff(col.offsets.to_numpy())
+        if (lengths != lengths[0]).any():
+            msg = "embedding column is ragged"
+            raise ValueError(msg)
+    emb = np.ascontiguousarray(flat.reshape(num_rows, -1), dtype=np.float32)
+    ids = np.ascontiguousarray(table[id_col].to_numpy(), dtype=np.int64)
+    texts = table[text_col].to_pylist() if text_col is not None and text_col in table.column_names else None
+    return emb, ids, texts
+
+
 class ItemProcessor:
     """Exact-search stand-in for ``xfmr_rec.data.lightning.ItemProcessor`` (search side only).
 
@@ -262,6 +296,78 @@ class ItemProcessor:
             self.item_ids = torch.as_tensor(item_ids, dtype=torch.int64).to(device).contiguous()
         self.item_text = item_text
         return self
+
+    def get_index_from_arrow(
+        self,
+        table,  # noqa: ANN001  pyarrow.Table
+        *,
+        embedding_col: str = "embedding",
+        device: torch.device | str = "cuda",
+        dtype: torch.dtype | None = None,
+        rank: int = 0,
+        world_size: int = 1,
+    ) -> ItemProcessor:
+        """Index from the item table the reference keeps in LanceDB: ``id_col``, ``text_col`` and a
+        ``fixed_size_list<float32, d>`` embedding column (data/lightning.py:189, :208-219).  ``rank`` / ``world_size``
+        keep only this rank's contiguous row shard (catalog row-sharding of ``distributed.sharded_topk``)."""
+        emb, ids, texts = arrow_to_catalog(table, id_col=self.id_col, text_col=self.text_col, embedding_col=embedding_col)
+        if world_size > 1:
+            bounds = [len(ids) * r // world_size for r in range(world_size + 1)]
+            lo, hi = bounds[rank], bounds[rank + 1]
+            emb, ids = emb[lo:hi], ids[lo:hi]
+            texts = texts[lo:hi] if texts is not None else None
+        emb_t = torch.from_numpy(emb)
+        if dtype is not None:
+            emb_t = emb_t.to(dtype)
+        return self.get_index(emb_t, torch.from_numpy(ids), texts, device=device)
+
+    def to_arrow(self):  # noqa: ANN201
+        """The index as a pyarrow table with the reference's column layout (``id_col``, ``text_col``, ``embedding``)."""
+        import pyarrow as pa  # noqa: PLC0415
+
+        if self.embeddings is None:
+            msg = "index is empty: call get_index first"
+            raise RuntimeError(msg)
+        emb = self.embeddings.float().cpu().numpy()
+        num_items, dim = emb.shape
+        ids = self.item_ids.cpu().numpy() if self.item_ids is not None else torch.arange(num_items).numpy()
+        columns = {self.id_col: pa.array(ids, type=pa.int64())}
+        if self.item_text is not None:
+            columns[self.text_col] = pa.array(list(self.item_text), type=pa.string())
+        columns["embedding"] = pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1), type=pa.float32()), dim)
+        return pa.table(columns)
+
+    def save(self, path) -> None:  # noqa: ANN001
+        """Write the index bundle: ``items.parquet`` (reference table layout) + ``processors.json`` with the
+        processor arguments under ``"items"`` (the key the reference's export uses, xfmr_rec/lightning.py:318-322)."""
+        import json  # noqa: PLC0415
+        import pathlib  # noqa: PLC0415
+
+        import pyarrow.parquet as pq  # noqa: PLC0415
+
+        path = pathlib.Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        pq.write_table(self.to_arrow(), path / ITEMS_PARQUET)
+        args = {"items": {"id_col": self.id_col, "text_col": self.text_col, "compute": self.compute}}
+        (path / PROCESSORS_JSON).write_text(json.dumps(args, indent=2))
+
+    @classmethod
+    def load(cls, path, *, device: torch.device | str = "cuda", dtype: torch.dtype | None = None,  # noqa: ANN001
+             rank: int = 0, world_size: int = 1) -> ItemProcessor:
+        """Read a bundle written by ``save`` (or any directory with an ``items.parquet`` in the reference's layout)."""
+        import json  # noqa: PLC0415
+        import pathlib  # noqa: PLC0415
+
+        import pyarrow.parquet as pq  # noqa: PLC0415
+
+        path = pathlib.Path(path)
+        args = {}
+        if (path / PROCESSORS_JSON).exists():
+            args = json.loads((path / PROCESSORS_JSON).read_text()).get("items", {})
+        known = {k: args[k] for k in ("id_col", "text_col", "compute") if k in args}
+        return cls(**known).get_index_from_arrow(
+            pq.read_table(path / ITEMS_PARQUET), device=device, dtype=dtype, rank=rank, world_size=world_size
+        )
 
     # exclusion lists go through a dense [Q, N] bit mask (exact for any list length) while that mask is small, and
     # through a post-filter of the k + E best otherwise (exact while k + E <= MAX_K) — see _exclusions

@@ -127,3 +127,26 @@ def test_metrics_known_answers() -> None:
     np.testing.assert_allclose(per_query[0].cpu().numpy(), want0, atol=1e-6)
     np.testing.assert_allclose(per_query[1].cpu().numpy(), [0.0] * 6, atol=0)
     np.testing.assert_allclose(mean.cpu().numpy(), np.array(want0) / 2, atol=1e-6)
+
+
+def test_index_bundle_round_trip_and_sharded_load(tmp_path) -> None:  # noqa: ANN001
+    """``save`` / ``load`` through the reference's table layout; a 2-way sharded load merges to the same answer."""
+    import xfmr_b200  # noqa: PLC0415
+    from oracle import native  # noqa: PLC0415
+
+    q, it = make(20, 1500, 32, 77)
+    ids = (torch.randperm(5000, generator=torch.Generator().manual_seed(3))[:1500] + 1)
+    texts = [f"item {int(i)}" for i in ids]
+    index = xfmr_b200.ItemProcessor(id_col="movie_id", text_col="movie_text").get_index(it, ids, texts)
+    index.save(tmp_path / "bundle")
+    loaded = xfmr_b200.ItemProcessor.load(tmp_path / "bundle")
+    assert loaded.id_col == "movie_id" and loaded.item_text == texts
+    s1, i1 = loaded.search_batch(q, None, top_k=15)
+    ref_s, ref_i = native.topk(q.numpy(), it.numpy(), 15, item_ids=ids.numpy())
+    assert np.array_equal(i1.cpu().numpy(), ref_i)
+    assert np.array_equal(s1.cpu().numpy(), ref_s)
+    frame = loaded.search(q[0].numpy(), None, top_k=3)
+    assert frame["movie_text"].tolist() == [f"item {int(i)}" for i in ref_i[0][:3]]
+    parts = [xfmr_b200.ItemProcessor.load(tmp_path / "bundle", rank=r, world_size=2).search_batch(q, None, top_k=15) for r in range(2)]
+    s2, i2 = xfmr_b200.topk_merge(torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1), 15)
+    assert torch.equal(i2, i1) and torch.equal(s2, s1)

@@ -92,3 +92,35 @@ def test_synthetic_inputs_follow_the_reference_layout() -> None:
     assert torch.allclose(inp["user_embed"].norm(dim=-1), torch.ones(64), atol=1e-5)   # models.py:59
     assert set(inp["target"].tolist()) <= {1.0, 2.0, 3.0, 4.0, 5.0}                    # ratings, params.py:8
     assert inp["item_idx"][64:].unique().numel() == 136                                  # negatives without replacement
+
+
+def test_arrow_catalog_adapter_reads_the_reference_table_layout(tmp_path) -> None:  # noqa: ANN001
+    """``movie_rn, movie_id, movie_text, embedding: fixed_size_list<float32, d>`` (data/lightning.py:208-219)."""
+    import numpy as np  # noqa: PLC0415
+    import pyarrow as pa  # noqa: PLC0415
+    import pyarrow.parquet as pq  # noqa: PLC0415
+
+    rng = np.random.default_rng(0)
+    emb = rng.standard_normal((37, 8)).astype(np.float32)
+    ids = rng.permutation(1000)[:37].astype(np.int64) + 1
+    texts = [f"movie {i}" for i in ids]
+    table = pa.table({
+        "movie_rn": pa.array(np.arange(1, 38), type=pa.int64()),
+        "movie_id": pa.array(ids),
+        "movie_text": pa.array(texts),
+        "embedding": pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1)), 8),
+    })
+    got_emb, got_ids, got_texts = xfmr_b200.arrow_to_catalog(table, id_col="movie_id", text_col="movie_text")
+    assert np.array_equal(got_emb, emb) and np.array_equal(got_ids, ids) and got_texts == texts
+    # through parquet (chunked columns) and with a variable-length list column
+    pq.write_table(table, tmp_path / "items.parquet", row_group_size=10)
+    back = pq.read_table(tmp_path / "items.parquet")
+    assert np.array_equal(xfmr_b200.arrow_to_catalog(back, id_col="movie_id", text_col=None)[0], emb)
+    as_list = table.set_column(3, "embedding", pa.array(emb.tolist(), type=pa.list_(pa.float32())))
+    assert np.array_equal(xfmr_b200.arrow_to_catalog(as_list, id_col="movie_id", text_col="movie_text")[0], emb)
+    ragged = table.set_column(3, "embedding", pa.array([[1.0]] * 36 + [[1.0, 2.0]], type=pa.list_(pa.float32())))
+    with pytest.raises(ValueError, match="ragged"):
+        xfmr_b200.arrow_to_catalog(ragged, id_col="movie_id", text_col=None)
+    # the index itself lives on the GPU: no CPU index
+    with pytest.raises((RuntimeError, AssertionError)):
+        xfmr_b200.ItemProcessor().get_index_from_arrow(table, device="cpu").search_batch(torch.zeros(1, 8), None, 5)
