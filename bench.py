@@ -356,6 +356,31 @@ def bench_mns(device: torch.device, world: int, rank: int) -> dict:
             "tensor_frac_of_sustained_peak": flops / (ms * 1e-3) / (pk["bf16_tflops_sustained"] * 1e12)}
 
 
+def bench_evaluate(device: torch.device) -> dict:
+    """Batched validation at MovieLens-1M shape: every user at once — exact top-20 with the user's
+    history excluded + the six ranking metrics — where the reference runs one user per step (lightning.py:149-206)."""
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    users, items, dim, k, hist, tgt = 6040, 3706, 64, 20, 165, 20
+    gen = torch.Generator(device=device).manual_seed(5)
+    catalog = synthetic.make_catalog(items, dim, seed=3, device=device)
+    queries = synthetic.make_catalog(users, dim, seed=4, device=device)
+    history = torch.randint(1, items + 1, (users, hist), generator=gen, device=device)
+    target_ids = torch.randint(1, items + 1, (users, tgt), generator=gen, device=device)
+    target_vals = torch.randint(1, 6, (users, tgt), generator=gen, device=device).float()
+    index = xfmr_b200.ItemProcessor().get_index(catalog, torch.arange(1, items + 1, device=device))
+
+    def step() -> None:
+        index.evaluate(queries, target_ids, target_vals, history, top_k=k)
+
+    t = timed_steps(step, 5, 3, None)
+    ms = statistics.median(t)
+    return {"metric": "batched_validation_users_per_s", "value": users / (ms * 1e-3), "unit": "users/s", "ms": ms,
+            "workload": f"C1-shaped: {users} users x {items} items, d={dim} fp32 (exact ids), top-{k}, {hist} excluded history "
+                        f"ids per user (dense mask), {tgt} graded targets per user, 6 metrics"}
+
+
 def bench_gather(device: torch.device) -> dict:
     import xfmr_b200  # noqa: PLC0415
 
@@ -508,6 +533,13 @@ def main() -> None:  # noqa: PLR0915
         torch.cuda.synchronize()
         e2e_eager_value = world * C2["batch"] * 20 / (time.perf_counter() - t0)
         e2e_run = e2e_run_graph
+    # what the host -> device path of this box delivers for exactly these buffers (explains e2e: it is copy-bound)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        upload()
+    torch.cuda.synchronize()
+    h2d_gbps = 10 * h2d_bytes / (time.perf_counter() - t0) / 1e9
     e2e_run(3)
     torch.cuda.synchronize()
     if world > 1:
@@ -548,7 +580,7 @@ def main() -> None:  # noqa: PLR0915
         },
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "eager_blocking_value": e2e_eager_value,
+                "eager_blocking_value": e2e_eager_value, "h2d_only_GBps": h2d_gbps,
                 "pipeline": ("eager module calls; the pinned-host upload of step i+1 runs on a copy stream under step i" if args.no_graph else
                              "xfmr_b200.GraphedLossStep: CUDA-graph replay; the pinned-host upload of step i+1 runs on a copy stream "
                              "under step i and the loss of step i-1 is read on the host while step i runs")},
@@ -576,6 +608,25 @@ def main() -> None:  # noqa: PLR0915
         per_loss["PairwiseHingeLoss[num_negatives=4]"] = {"ms_per_step": statistics.median(t),
                                                            "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
 
+        hard = xfmr_b200.PairwiseHingeLoss(num_negatives=4, sigma=SIGMA, margin=MARGIN, mining="hard")
+        t = timed_steps(graphed(loss_step_fn(hard, inp)), 8, 3, flush_buf)
+        per_loss["PairwiseHingeLoss[num_negatives=4, mining=hard]"] = {"ms_per_step": statistics.median(t),
+                                                                        "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
+        directau = xfmr_b200.DirectAULoss(gamma=1.0, t=2.0)
+        t = timed_steps(graphed(loss_step_fn(directau, inp)), 8, 3, flush_buf)
+        per_loss["DirectAULoss"] = {"ms_per_step": statistics.median(t), "samples_per_s": C2["batch"] / (statistics.median(t) * 1e-3)}
+        for n_rows in (C2["batch"], C2["num_items"]):
+            x = inp["item_embed"][:n_rows].detach().requires_grad_(True)
+
+            def uni_step(x=x) -> tuple:  # noqa: ANN001
+                loss = xfmr_b200.uniformity_loss(x, 2.0)
+                return loss, torch.autograd.grad(loss, x)[0]
+
+            t = timed_steps(graphed(uni_step), 8, 3, flush_buf)
+            ms = statistics.median(t)
+            # one sweep of 2 tile-MMAs per tile pair does forward and backward: 4 n^2 d algorithmic flops
+            per_loss[f"uniformity_loss[n={n_rows}]"] = {"ms_per_step": ms, "tflops": 4.0 * n_rows * n_rows * C2["dim"] / (ms * 1e-3) / 1e12}
+
         def fused_fwd() -> None:
             xfmr_b200.fused_losses(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"],
                                    pos_idx=inp["pos_idx"], sigma=SIGMA, margin=MARGIN)
@@ -589,6 +640,7 @@ def main() -> None:  # noqa: PLR0915
         torch.cuda.empty_cache()
         line["retrieval"] = bench_retrieval(device, world, rank, args.retrieval_items, args.retrieval_queries, 100)
         if rank == 0:
+            line["evaluate"] = bench_evaluate(device)
             line["gather"] = bench_gather(device)
             base = cpu_reference_rate(2, 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
