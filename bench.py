@@ -421,13 +421,15 @@ def main() -> None:  # noqa: PLR0915
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the one JSON line and nothing else: native libraries write there too (NCCL prints its version
+    # banner with printf at NCCL_DEBUG=VERSION and WARN), so file descriptor 1 points at stderr until the line is ready
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     warmup = max(args.warmup, 3)
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -649,7 +651,9 @@ def main() -> None:  # noqa: PLR0915
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        print(json.dumps(line))  # noqa: T201
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
