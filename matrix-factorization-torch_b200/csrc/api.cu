@@ -1089,9 +1089,22 @@ int xb_hash_gather(const int64_t* ids, int64_t n, int32_t num_hashes, uint32_t s
   const int vec_per_row = dim / 8;
   int lpr = 1;
   while (lpr < vec_per_row && lpr < 32) lpr <<= 1;
-  hash_gather_kernel<<<cdiv(n * lpr, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(ids), n, num_hashes, seed0, static_cast<const uint4*>(table), row_mask, dim,
-      static_cast<uint4*>(out), idx_out, lpr);
+  // (the compile-time-k variants take two ids per thread)
+  const long long n_threads = (num_hashes <= 4 ? (n + 1) / 2 : n) * lpr;
+  const dim3 grid(cdiv(n_threads, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define XB_GATHER(NH)                                                                                              \
+  hash_gather_kernel<NH><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(ids), n, num_hashes, seed0,      \
+                                               static_cast<const uint4*>(table), row_mask, dim,                    \
+                                               static_cast<uint4*>(out), idx_out, lpr)
+  switch (num_hashes) {
+    case 1: XB_GATHER(1); break;
+    case 2: XB_GATHER(2); break;
+    case 3: XB_GATHER(3); break;
+    case 4: XB_GATHER(4); break;
+    default: XB_GATHER(0); break;
+  }
+#undef XB_GATHER
   XB_LAUNCHED();
   return XB_OK;
 }

@@ -1190,15 +1190,60 @@ __global__ void hash_indices_kernel(const long long* __restrict__ ids, long long
 // `LPR` lanes cooperate on one id: each lane owns 8 bf16 (16 bytes) of the row per pass.
 // dim % 8 == 0.  Table rows are fetched with 128-bit read-only loads, the output row is written with
 // 128-bit streaming stores; the sum is fp32 with a single final rounding (embedding_bag(mode="sum")).
+// NH > 0: number of hashes known at compile time — all NH row loads of a lane are issued before the first add, so
+// twice (k = 2) the bytes are in flight per thread (the kernel is latency-bound otherwise: 2,048 threads x 16 B per
+// SM is less than the ~35 KB per SM that HBM latency x bandwidth asks for).  NH = 0: run-time `nh`.
+template <int NH>
 __global__ void hash_gather_kernel(const long long* __restrict__ ids, long long n, int nh, uint32_t seed0,
                                    const uint4* __restrict__ table, uint32_t row_mask, int dim,
                                    uint4* __restrict__ out, int* __restrict__ idx_out, int lpr) {
   const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long item = gt / lpr;
   const int sub = static_cast<int>(gt % lpr);
-  if (item >= n) return;
+  if (item >= (NH > 0 ? (n + 1) >> 1 : n)) return;
   const int vec_per_row = dim >> 3;
   const long long id = ids[item];
+  if constexpr (NH > 0) {
+    // two ids per thread (`item` and `item + n_half`): 2 * NH independent 16-byte loads in flight
+    const long long n_half = (n + 1) >> 1;
+    const long long item2 = item + n_half;
+    const bool two = item2 < n;
+    const long long id2 = two ? ids[item2] : id;
+    uint32_t r[2][NH > 0 ? NH : 1];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      r[0][h] = xxh32_i64(id, seed0 + h) & row_mask;
+      r[1][h] = xxh32_i64(id2, seed0 + h) & row_mask;
+      if (idx_out != nullptr && sub == 0) {
+        idx_out[item * NH + h] = static_cast<int>(r[0][h]);
+        if (two) idx_out[item2 * NH + h] = static_cast<int>(r[1][h]);
+      }
+    }
+    for (int vcol = sub; vcol < vec_per_row; vcol += lpr) {
+      uint4 t[2][NH > 0 ? NH : 1];
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) t[e][h] = __ldg(table + static_cast<size_t>(r[e][h]) * vec_per_row + vcol);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {   // hash order: the fp32 sum is embedding_bag(mode="sum")'s
+          acc[0] += bf_lo(t[e][h].x); acc[1] += bf_hi(t[e][h].x);
+          acc[2] += bf_lo(t[e][h].y); acc[3] += bf_hi(t[e][h].y);
+          acc[4] += bf_lo(t[e][h].z); acc[5] += bf_hi(t[e][h].z);
+          acc[6] += bf_lo(t[e][h].w); acc[7] += bf_hi(t[e][h].w);
+        }
+        if (e == 0 || two)
+          __stcs(out + static_cast<size_t>(e == 0 ? item : item2) * vec_per_row + vcol,
+                 make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                            pack_bf16x2(acc[6], acc[7])));
+      }
+    }
+  } else {
   for (int vcol = sub; vcol < vec_per_row; vcol += lpr) {
     float acc[8];
 #pragma unroll
@@ -1218,6 +1263,7 @@ __global__ void hash_gather_kernel(const long long* __restrict__ ids, long long 
     o.z = pack_bf16x2(acc[4], acc[5]);
     o.w = pack_bf16x2(acc[6], acc[7]);
     __stcs(out + static_cast<size_t>(item) * vec_per_row + vcol, o);
+  }
   }
 }
 
