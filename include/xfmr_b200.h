@@ -13,8 +13,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
  *   - the caller owns every buffer, including the workspace (size from the matching *_workspace_bytes);
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no
- *     default-stream use, no allocation: calls are CUDA-graph capturable;
+ *   - all work is ordered on `stream` (a cudaStream_t passed as void*); no host synchronisation, no
+ *     default-stream use, no memory allocation: calls are CUDA-graph capturable.  xb_loss_forward runs its
+ *     mask builder on a library-owned helper stream that forks from `stream` and joins back into it with
+ *     events before the call returns to it (XB_FORK=0 keeps everything on `stream`);
  *   - return value: 0 = ok, < 0 = error code below; xb_last_error_string() describes the last failure on
  *     the calling thread.  Nothing throws or aborts across the ABI;
  *   - there is no CPU path: a build without a GPU still loads, but every compute entry point needs sm_100.

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +78,45 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
 // debug trace target (set by xb_debug_set_trace; nullptr = off)
 static std::atomic<long long*> g_trace{nullptr};
 static std::atomic<int> g_trace_tiles{0};
+
+// A library-owned helper stream per device.  Independent pieces of one call (the false-negative mask builder vs the
+// operand preparation) fork from the caller's stream and join back into it through events, so the call stays ordered
+// on - and capturable from - the caller's stream while its small latency-bound kernels overlap.  XB_FORK=0 disables it.
+struct SideLane {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool tried = false, ok = false;
+};
+static std::mutex g_side_mutex;
+static SideLane g_side[64];
+static SideLane* side_lane() {
+  static const bool enabled = [] {
+    const char* e = std::getenv("XB_FORK");
+    return e == nullptr || e[0] != '0';
+  }();
+  int dev = -1;
+  if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_side_mutex);
+  SideLane& l = g_side[dev];
+  if (!l.tried) {
+    l.tried = true;
+    l.ok = cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!l.ok) (void)cudaGetLastError();
+  }
+  return l.ok ? &l : nullptr;
+}
+// fork: everything enqueued on `st` so far happens before what follows on the helper stream (record + wait are
+// issued under the lock so that two host threads cannot interleave their pairs)
+static bool side_fork(SideLane* l, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_side_mutex);
+  return cudaEventRecord(l->fork, st) == cudaSuccess && cudaStreamWaitEvent(l->s, l->fork, 0) == cudaSuccess;
+}
+static bool side_join(SideLane* l, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_side_mutex);
+  return cudaEventRecord(l->join, l->s) == cudaSuccess && cudaStreamWaitEvent(st, l->join, 0) == cudaSuccess;
+}
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -397,6 +437,13 @@ static int check_loss_desc(const xb_loss_desc* d) {
 template <typename T>
 static int prep_operand(const void* x, int n, int d, int kp, int parts, void* out, float* norm2, void* aug,
                         cudaStream_t st) {
+  if (sizeof(T) == 2 && parts == 1 && (d & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    prep_operand_bf16_kernel<<<cdiv(static_cast<long long>(cdiv(n, 4)) * 32, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), n, d, kp, static_cast<__nv_bfloat16*>(out), norm2,
+        static_cast<__nv_bfloat16*>(aug));
+    XB_LAUNCHED();
+    return XB_OK;
+  }
   prep_operand_kernel<T><<<cdiv(static_cast<long long>(n) * 32, 256), 256, 0, st>>>(
       static_cast<const T*>(x), n, d, kp, parts, static_cast<__nv_bfloat16*>(out), norm2,
       static_cast<__nv_bfloat16*>(aug));
@@ -646,6 +693,18 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
   const int B = desc->batch, N = desc->num_items, d = desc->dim;
   const float* lq = desc->has_log_q ? log_q : nullptr;
 
+  // 0. false-negative mask (losses.py:92-110) and its transpose: depends on the ids only, so it runs on the helper
+  //    stream beside the operand preparation and joins before the first sweep
+  const int lm = sweep_lm_from_mask(desc->loss_mask);
+  SideLane* lane = lm != 0 ? side_lane() : nullptr;
+  if (lane != nullptr && !side_fork(lane, st)) return fail(XB_ERR_CUDA, "stream fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (lm != 0) {
+    rc = build_pair_mask(B, N, desc->num_pos, reinterpret_cast<const long long*>(item_idx),
+                         reinterpret_cast<const long long*>(item_idx), reinterpret_cast<const long long*>(pos_idx),
+                         reinterpret_cast<uint32_t*>(ws + w.mask), reinterpret_cast<uint32_t*>(ws + w.mask_t),
+                         ws + w.pm_ws, lane != nullptr ? lane->s : st);
+    if (rc != XB_OK) return rc;
+  }
   // 1. operands -> bf16 (hi [, lo]) + norms
   if (desc->in_dtype == XB_DTYPE_F32) {
     if ((rc = prep_operand<float>(user_embed, B, d, w.kp, w.parts, ws + w.qprep, reinterpret_cast<float*>(ws + w.qn2), ws + w.qaug, st))) return rc;
@@ -665,17 +724,11 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                                    reinterpret_cast<float2*>(ws + w.ipar));
   XB_LAUNCHED();
 
-  const int lm = sweep_lm_from_mask(desc->loss_mask);
+  if (lane != nullptr && !side_join(lane, st)) return fail(XB_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
   float4* rowstat = reinterpret_cast<float4*>(ws + w.rowstat);
   float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
   if (lm != 0) {
-    // 3. false-negative mask (losses.py:92-110) and its transpose
-    rc = build_pair_mask(B, N, desc->num_pos, reinterpret_cast<const long long*>(item_idx),
-                         reinterpret_cast<const long long*>(item_idx), reinterpret_cast<const long long*>(pos_idx),
-                         reinterpret_cast<uint32_t*>(ws + w.mask), reinterpret_cast<uint32_t*>(ws + w.mask_t),
-                         ws + w.pm_ws, st);
-    if (rc != XB_OK) return rc;
-    // 4. the sweep
+    // 3. the sweep
     CUtensorMap tmQ, tmI, tmQa, tmIa;
     if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
     if ((rc = make_operand_map(&tmI, ws + w.iprep, N, static_cast<long long>(w.parts) * w.kp))) return rc;

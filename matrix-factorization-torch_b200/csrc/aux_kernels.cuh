@@ -77,6 +77,59 @@ __global__ void prep_operand_kernel(const T* __restrict__ x, int n, int d, int k
   }
 }
 
+// bf16 in, bf16 out (parts = 1, d % 8 == 0, 16-byte aligned rows): a half-warp per row with 128-bit loads and stores,
+// two rows per half-warp so that every lane has two independent loads in flight (the one-warp-per-row kernel above
+// moves 16 KB per SM at a time and is latency-bound at 2.6 TB/s).
+__global__ void prep_operand_bf16_kernel(const __nv_bfloat16* __restrict__ x, int n, int d, int kp,
+                                         __nv_bfloat16* __restrict__ out, float* __restrict__ norm2,
+                                         __nv_bfloat16* __restrict__ aug) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 15;
+  const int row0 = warp * 4 + (lane >> 4) * 2;
+  float acc[2] = {0.f, 0.f};
+  for (int k = sub * 8; k < kp; k += 128) {
+    uint4 t[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      t[r] = make_uint4(0u, 0u, 0u, 0u);
+      if (row0 + r < n && k < d) t[r] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row0 + r) * d + k);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (row0 + r >= n) continue;
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + r) * kp + k) = t[r];
+      const float e0 = bf_lo(t[r].x), e1 = bf_hi(t[r].x), e2 = bf_lo(t[r].y), e3 = bf_hi(t[r].y);
+      const float e4 = bf_lo(t[r].z), e5 = bf_hi(t[r].z), e6 = bf_lo(t[r].w), e7 = bf_hi(t[r].w);
+      float a = acc[r];
+      a = fmaf(e0, e0, a); a = fmaf(e1, e1, a); a = fmaf(e2, e2, a); a = fmaf(e3, e3, a);
+      a = fmaf(e4, e4, a); a = fmaf(e5, e5, a); a = fmaf(e6, e6, a); a = fmaf(e7, e7, a);
+      acc[r] = a;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);   // stays inside the half-warp
+    const int row = row0 + r;
+    if (row >= n) continue;
+    if (sub == 0 && norm2 != nullptr) norm2[row] = acc[r];
+    if (aug != nullptr) {
+      const float h = -0.5f * acc[r];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(h);
+      const float r1 = h - __bfloat162float(h0);
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+      const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+      const int k = sub;
+      const __nv_bfloat16 vr = k < 3 ? one : (k == 3 ? h0 : (k == 4 ? h1 : (k == 5 ? h2 : zero)));
+      const __nv_bfloat16 vc = k == 0 ? h0 : (k == 1 ? h1 : (k == 2 ? h2 : (k < 6 ? one : zero)));
+      aug[static_cast<size_t>(row) * 32 + k] = vr;
+      aug[static_cast<size_t>(row) * 32 + 16 + k] = vc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-query and per-item parameters of the logit map (see sweep.cuh).  One warp per row.
 //   rowinfo[i] = {sign, |target|, target, L2_ii}       diag[i] = S_ii = -|q_i - v_i|^2 / 2
