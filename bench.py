@@ -224,6 +224,28 @@ def cpu_reference_rate(steps: int, warmup: int, name: str = HEADLINE_LOSS) -> di
     }
 
 
+def aten_gpu_reference_rate(device: torch.device, name: str = HEADLINE_LOSS) -> dict:
+    """The same restatement of the reference's algorithm with CUDA tensors: what the reference's ATen-composed loss costs
+    on this very GPU (SURVEY.md 8d "ATen-on-GPU bar").  Part of the baseline leg: the port is the thing measured here,
+    never the product.  Bounded sample like the CPU leg (the B x N x P mask broadcast is 11.5 GB at full N)."""
+    from oracle import losses_oracle  # noqa: PLC0415
+    from xfmr_b200 import synthetic  # noqa: PLC0415
+
+    n_sample = 8192
+    inp = synthetic.make_loss_inputs(C2["batch"], n_sample, C2["dim"], C2["num_pos"], n_catalog=C2["num_items"], seed=0,
+                                     device=device)
+
+    def run() -> None:
+        losses_oracle.losses_and_grads(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"],
+                                       pos_idx=inp["pos_idx"], sigma=SIGMA, margin=MARGIN, names=(name,))
+
+    ms = statistics.median(timed_steps(run, 5, 2, None))
+    scale = C2["num_items"] / n_sample
+    return {"value": C2["batch"] / (ms * 1e-3 * scale), "unit": UNIT, "kind": "port on cuda (ATen kernels, fp32)",
+            "sample": f"{name} fwd+bwd, B={C2['batch']} x N_s={n_sample} of {C2['num_items']} items, d={C2['dim']}, P={C2['num_pos']}: "
+                      f"{ms:.2f} ms; rate scaled by N_s/N"}
+
+
 def run_reference(args: argparse.Namespace) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -646,6 +668,7 @@ def main() -> None:  # noqa: PLR0915
             line["gather"] = bench_gather(device)
             base = cpu_reference_rate(2, 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["aten_gpu_baseline"] = aten_gpu_reference_rate(device)
     elif rank == 0:
         base = cpu_reference_rate(1, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
