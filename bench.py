@@ -310,10 +310,45 @@ def bench_retrieval(device: torch.device, world: int, rank: int, num_items_total
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
+    # the same search with 64 excluded ids per query: the 64 best items of every query are excluded, through
+    # the sparse path (rank k + 64 per shard, drop the listed ids, keep k) - a dense Q x N mask would be 819 GB here
+    n_excl = 64
+
+    def search_excl(qs: torch.Tensor, kk: int) -> tuple[torch.Tensor, torch.Tensor]:
+        s_, i_ = xfmr_b200.topk_search(qs, items, kk + n_excl, id_base=rank * shard)
+        return xfmr_b200.topk_filter(s_, i_, excl, kk)
+
+    def step_excl() -> tuple[torch.Tensor, torch.Tensor]:
+        if world > 1:
+            return xfmr_b200.distributed.sharded_topk(search_excl, xfmr_b200.topk_merge, queries, k)
+        return search_excl(queries, k)
+
+    if world > 1:
+        _, excl = xfmr_b200.distributed.sharded_topk(search, xfmr_b200.topk_merge, queries, n_excl)
+    else:
+        _, excl = search(queries, n_excl)
+    excl = excl.contiguous()
+    step_excl()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, ids_excl = step_excl()
+    e1.record()
+    e1.synchronize()
+    ms_excl = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_excl, op=dist.ReduceOp.MAX)
+    ms_excl = float(ms_excl)
+    sample = slice(0, 512)
+    leaked = bool((ids_excl[sample, :, None] == excl[sample, None, :]).any())
+    assert not leaked, "an excluded id came back"
     flops = 2.0 * num_queries * shard * 128
     pk = peaks()
     del items
     return {"metric": "exact_top100_queries_per_s", "value": num_queries / (ms * 1e-3), "unit": "queries/s",
+            "with_64_exclusions_per_query": {"value": num_queries / (ms_excl * 1e-3), "unit": "queries/s", "ms": ms_excl},
             "workload": f"{num_queries} queries x {num_items_total} items (sharded {world} ways), d=128 bf16, k={k}",
             "ms": ms, "scaling": "strong", "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "tensor_frac_of_sustained_peak": flops / (ms * 1e-3) / (pk["bf16_tflops_sustained"] * 1e12),
