@@ -358,7 +358,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->Kf = w->K + MINE_OVERFETCH;
   const int lm = sweep_lm_from_mask(d->loss_mask);
   const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
-  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, true, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 0, true) : 0);
+  w->fwd = plan_sweep(B, N, w->kp, w->parts, false, true, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 1, true) : 0);
   w->gq = plan_sweep(B, N, w->kp, w->parts, true, true, 2);
   w->fq = plan_sweep(B, N, w->kp, w->parts, true, true, 6);
   w->gi = plan_sweep(N, B, w->kp, w->parts, true, true, gq_floats);
@@ -790,7 +790,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         p.topk_mining = hard ? 3 : 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
         cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
-            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 0, true), p.cap, w.Kf, p.cand, p.cand_cnt,
+            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 1, true), p.cap, w.Kf, p.cand, p.cand_cnt,
             reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
         XB_LAUNCHED();
       }

@@ -71,6 +71,7 @@ enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 
 __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
 // number of epilogue column parts of a kernel variant
 __host__ __device__ constexpr int epi_parts(int mode, int lm, bool /*qrow*/) {
+  // (TOPK with 4 parts was measured: the 104-register cap of a 608-thread CTA spills the selection state, 3x slower)
   return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/ || mode == 4 /*FWDQ*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
 }
 // threads per CTA: epilogue warps + TMA producer warp + two MMA issuer warps
