@@ -196,10 +196,8 @@ def _(workspace, d_losses, batch, num_items, dim, num_pos, bf16_io, has_log_q, n
 def _setup_context(ctx, inputs, output) -> None:  # noqa: ANN001
     user_embed, item_embed, _target, _item_idx, pos_idx, log_q, num_negatives, sigma, margin, loss_mask, compute, mining = inputs
     _losses, workspace = output
-    import os  # noqa: PLC0415
-    if os.environ.get("XB_AB", "1") == "1":
-        ctx.mark_non_differentiable(workspace)
-        ctx.set_materialize_grads(False)  # never allocate a zero "gradient" for the workspace bytes
+    ctx.mark_non_differentiable(workspace)
+    ctx.set_materialize_grads(False)  # never allocate a zero "gradient" for the workspace bytes
     ctx.save_for_backward(workspace)
     ctx.meta = (
         user_embed.size(0),
