@@ -62,67 +62,80 @@ def ncu_traffic() -> float | None:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every few milliseconds from
+    a thread between ``mark_begin`` and ``mark_end`` (the timed region lasts ~0.1 s, too short for ``nvidia-smi -lms``
+    to be sure of a sample), plus one sample taken by the caller itself while the GPU is still busy."""
 
-    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index: int) -> None:
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.path = pathlib.Path(f"/tmp/xb_clocks_{os.getpid()}.csv")  # noqa: S108
-        self.t_begin = 0.0
-        self.t_end = 0.0
+        import threading  # noqa: PLC0415
+
+        self.handle = None
+        self.nvml = None
+        self.samples: list[tuple[float, int]] = []
+        self.max_mhz = None
+        self._run = threading.Event()
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        try:
+            import pynvml  # noqa: PLC0415
+
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(gpu_index)
+            try:
+                bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.handle = None
+
+    def sample(self) -> None:
+        if self.handle is None:
+            return
+        try:
+            mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            try:
+                bits = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                bits = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((mhz, bits))
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+    def _poll(self) -> None:
+        while not self._stop.is_set():
+            if self._run.is_set():
+                self.sample()
+            time.sleep(0.004)
 
     def start(self) -> None:
-        """Start sampling; nvidia-smi needs a moment before its first line, so call this ahead of the region."""
-        try:
-            self.proc = subprocess.Popen(  # noqa: S603
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",  # noqa: S607
-                 "-i", str(self.gpu_index)],
-                stdout=self.path.open("w"), stderr=subprocess.DEVNULL,
-            )
-        except OSError:
-            self.proc = None
+        if self.handle is not None:
+            self._thread.start()
 
     def mark_begin(self) -> None:
-        self.t_begin = time.time()
+        self.samples.clear()
+        self._run.set()
 
     def mark_end(self) -> None:
-        self.t_end = time.time()
+        """Call while the last timed step is still in flight (before the final synchronize)."""
+        self.sample()
+        self._run.clear()
 
     def stop(self) -> None:
-        if self.proc is not None:
-            time.sleep(0.12)
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
+        self._stop.set()
+        if self._thread.is_alive():
+            self._thread.join(timeout=1)
 
     def summary(self) -> dict:
-        """Median SM clock and the throttle reasons seen INSIDE [mark_begin, mark_end] (+- one sample)."""
-        import datetime  # noqa: PLC0415
-
-        sm, mx, reasons = [], [], set()
-        if self.path.exists():
-            for line in self.path.read_text().splitlines():
-                cols = [c.strip() for c in line.split(",")]
-                if len(cols) < 9:  # noqa: PLR2004
-                    continue
-                try:
-                    stamp = datetime.datetime.strptime(cols[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()  # noqa: DTZ007
-                    if not (self.t_begin - 0.06 <= stamp <= self.t_end + 0.06):  # noqa: PLR2004
-                        continue
-                    sm.append(float(cols[1]))
-                    mx.append(float(cols[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), cols[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            self.path.unlink(missing_ok=True)
-        busy = [x for x in sm if x > 0]
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [m for m, _ in self.samples if m > 0]
+        reasons = sorted({name for _, bits in self.samples for bit, name in self.REASONS.items() if bits & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml"}
 
 
 def flush_l2(buf: torch.Tensor) -> None:

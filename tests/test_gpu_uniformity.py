@@ -38,6 +38,8 @@ def oracle_uniformity(x: torch.Tensor, t: float) -> tuple[float, torch.Tensor]:
     (1000, 128, 2.0, 1.0),
     (1024, 64, 0.5, 1.0),
     (3000, 48, 5.0, 0.1),     # d not a multiple of 64, several row blocks and column chunks
+    (600, 64, 60.0, 0.05),    # sigma = 120: rows whose exponent reference is far from the first tile's maximum
+    (400, 32, 400.0, 0.02),   # sigma = 800: the device-side fallback sweeps (fixed reference out of fp32 range)
 ])
 def test_uniformity_fp32(n: int, d: int, t: float, spread: float) -> None:
     import xfmr_b200  # noqa: PLC0415
