@@ -116,3 +116,57 @@ def test_sharded_topk_equals_unsharded() -> None:
     out = manager.dict()
     mp.spawn(_sharded_topk_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _sharded_exclusions_worker(rank: int, world: int, port: int, out: dict) -> None:
+    """Exclusion lists are applied shard-locally (rank the k + E best of the shard, drop the listed ids, keep k) and the
+    filtered lists are merged: must equal the global pre-filtered top-k (data/lightning.py:247-252)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import xfmr_b200  # noqa: PLC0415
+    from oracle import native  # noqa: PLC0415
+
+    rng = np.random.default_rng(11)
+    queries = rng.standard_normal((13, 8)).astype(np.float32)
+    catalog = rng.standard_normal((90, 8)).astype(np.float32)
+    full = queries @ catalog.T
+    excl = np.full((13, 6), native.PAD_ID, dtype=np.int64)
+    for r in range(13):
+        excl[r, : r % 6] = np.argsort(-full[r])[: r % 6]          # 0..5 of the best items, ragged
+    bounds = np.linspace(0, 90, world + 1).astype(int)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n_excl = excl.shape[1]
+
+    def search(q: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        # the shard-local sparse path of ItemProcessor.search_batch: rank k + E, then filter (python stand-in for xb_topk_filter)
+        s, i = native.topk(q.numpy(), catalog[lo:hi], k + n_excl, id_base=int(lo))
+        rows_s, rows_i = [], []
+        for r in range(s.shape[0]):
+            banned = set(excl[r].tolist())
+            kept = [(float(a), int(b)) for a, b in zip(s[r], i[r]) if int(b) >= 0 and int(b) not in banned][:k]
+            kept += [(float("-inf"), -1)] * (k - len(kept))
+            rows_s.append([p[0] for p in kept])
+            rows_i.append([p[1] for p in kept])
+        return torch.tensor(rows_s), torch.tensor(rows_i)
+
+    def merge(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        rows_s, rows_i = [], []
+        for r in range(scores.size(0)):
+            pairs = sorted(((-float(s), int(i)) for s, i in zip(scores[r], ids[r]) if int(i) >= 0))[:k]
+            rows_s.append([-p[0] for p in pairs])
+            rows_i.append([p[1] for p in pairs])
+        return torch.tensor(rows_s), torch.tensor(rows_i)
+
+    s, i = xfmr_b200.distributed.sharded_topk(search, merge, torch.from_numpy(queries), 5)
+    ref_s, ref_i = native.topk(queries, catalog, 5, exclude=excl)
+    out[rank] = bool(np.array_equal(i.numpy(), ref_i) and np.array_equal(s.numpy().astype(np.float32), ref_s))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_local_exclusions_equal_the_global_prefilter() -> None:
+    world = 2
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_sharded_exclusions_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
