@@ -898,11 +898,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // The vote evaluates u = wa * S + wb per element (wa = +-a2) and tests |u| <= whalf for a two-sided window,
     // u <= whalf for a one-sided one (`wone`); whalf carries a rounding slack, the exact key decides on the append path.
     float wa = rp_reg[0], wb = 0.f, whalf = -1.f;
-    bool wopen = false, wone = false;
+    bool wopen = false, wone = false, wneg = false;   // wneg: u is evaluated on -R (wa = -a2)
     auto set_window = [&]() {
       const float a2 = rp_reg[0], c0 = rp_reg[2];
       wopen = false;
       wone = true;
+      wneg = false;
       wa = a2;
       wb = 0.f;
       whalf = -1.f;
@@ -912,6 +913,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if (thr == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }   // no threshold yet
       const float slack = 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
       if (mode == 3) {                              // R >= rt  <=>  -(R - rt) <= 0
+        wneg = true;
         wa = -a2;
         wb = rt - c0;
         whalf = slack;
@@ -920,6 +922,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         wb = c0 - (mode == 2 ? -0.5f * rt : 0.5f * rt);
         whalf = -0.5f * rt + slack;
       } else if (mode == 2) {                       // -R <= rt
+        wneg = true;
         wa = -a2;
         wb = -c0 - rt;
         whalf = slack;
@@ -1229,7 +1232,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                 //  per-tile barrier, so a compacting warp never stalls the others)
                 const int jc = min(j0 + ucol + c, p.nC - 1);
                 const float lq = __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
-                x -= (wa == rp_reg[0]) ? lq : -lq;
+                x -= wneg ? -lq : lq;
               }
               return x;
             };

@@ -188,6 +188,12 @@ def test_log_q_extension_matches_oracle() -> None:
     got_k = cuda_losses_and_grads(inp, num_negatives=5, sigma=3.0, margin=0.5, log_q=inp["log_q"])
     ref_k = oracle_losses_and_grads(inp, num_negatives=5, sigma=3.0, margin=0.5, log_q=inp["log_q"])
     assert_close(got_k, ref_k, label="log_q K=5")
+    # signed targets flip the logit sign per row; hard mining with LogQ exercises the one-sided vote on -R
+    signed = synthetic.make_loss_inputs(150, 800, 64, 6, n_catalog=300, seed=12, signed_targets=True)
+    for mining in ("semi_hard", "hard"):
+        got_s = cuda_losses_and_grads(signed, num_negatives=7, sigma=3.0, margin=0.5, log_q=signed["log_q"], mining=mining)
+        ref_s = oracle_losses_and_grads(signed, num_negatives=7, sigma=3.0, margin=0.5, log_q=signed["log_q"], mining=mining)
+        assert_close(got_s, ref_s, label=f"log_q K=7 signed {mining}")
 
 
 def test_config1_movielens_1m_shape_fp32() -> None:
