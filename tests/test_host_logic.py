@@ -124,3 +124,23 @@ def test_arrow_catalog_adapter_reads_the_reference_table_layout(tmp_path) -> Non
     # the index itself lives on the GPU: no CPU index
     with pytest.raises((RuntimeError, AssertionError)):
         xfmr_b200.ItemProcessor().get_index_from_arrow(table, device="cpu").search_batch(torch.zeros(1, 8), None, 5)
+
+
+def test_reference_arm_prints_one_contract_line() -> None:
+    """``bench.py --impl reference``: the CPU port timed on the host cores, one JSON line with the contract keys."""
+    import json  # noqa: PLC0415
+    import pathlib  # noqa: PLC0415
+    import subprocess  # noqa: PLC0415
+    import sys  # noqa: PLC0415
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],  # noqa: S603
+                         capture_output=True, text=True, check=True, timeout=600)
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "fused_loss_fwd_bwd_samples_per_s" and line["unit"] == "samples/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["vs_baseline"] is None
