@@ -4,9 +4,9 @@ The C-ABI entry points allocate nothing and never synchronise (``include/xfmr_b2
 forward + backward is capturable as one CUDA graph.  ``GraphedLossStep`` does the capture once for a fixed
 input shape and then serves steps from either device tensors or pinned host tensors:
 
-* host inputs are uploaded on a copy stream into one of two staging slots, so the upload of step ``i + 1`` runs
-  under the graph replay of step ``i`` (what a training loop's prefetching data loader does for the reference's
-  ``training_step``, ``xfmr_rec/lightning.py:189-192``);
+* host inputs are uploaded on a copy stream into one of three input slots, each with its own captured graph, so the
+  upload of step ``i + 1`` runs under the graph replay of step ``i`` (what a training loop's prefetching data loader
+  does for the reference's ``training_step``, ``xfmr_rec/lightning.py:189-192``) and no staging copy is needed;
 * the step's loss is copied back to pinned host memory asynchronously; ``StepResult.loss_value()`` waits for
   that copy only, so a caller can read step ``i - 1`` while step ``i`` is in flight.
 
@@ -26,7 +26,7 @@ _INPUT_KEYS = ("user_embed", "item_embed", "target", "item_idx", "pos_idx")
 
 
 class StepResult:
-    """Handle of one submitted step: static output tensors + the host copy of its loss."""
+    """Handle of one submitted step: the slot's output tensors + the host copy of its loss."""
 
     def __init__(self, step: GraphedLossStep, slot: int, done: torch.cuda.Event) -> None:
         self._step = step
@@ -40,20 +40,25 @@ class StepResult:
 
     @property
     def d_user(self) -> torch.Tensor:
-        """Static gradient buffer (overwritten by the next step)."""
-        return self._step.d_user
+        """Gradient buffer of the slot (overwritten when the slot comes round again, ``NUM_SLOTS`` steps later)."""
+        return self._step._outputs[self._slot][1]  # noqa: SLF001
 
     @property
     def d_item(self) -> torch.Tensor:
-        return self._step.d_item
+        return self._step._outputs[self._slot][2]  # noqa: SLF001
 
 
 class GraphedLossStep:
-    """``module(user_embed, item_embed, target, item_idx=, pos_idx=)`` + backward as one CUDA graph.
+    """``module(user_embed, item_embed, target, item_idx=, pos_idx=)`` + backward as a CUDA graph per input slot.
 
     ``example`` fixes shapes and dtypes (a dict with the five input tensors on the GPU).  ``submit(inputs)``
-    takes a dict of the same tensors on the GPU or in (pinned) host memory.
+    takes a dict of the same tensors on the GPU or in (pinned) host memory.  There are ``NUM_SLOTS`` input slots, each
+    with its own captured graph reading the slot's tensors in place (no device-to-device staging copy): uploads land
+    in the slot that was used ``NUM_SLOTS`` steps ago while the graphs of the slots in between run.  Results stay
+    valid until their slot is reused.
     """
+
+    NUM_SLOTS = 3
 
     def __init__(self, module: EmbeddingLoss, example: dict[str, torch.Tensor]) -> None:
         device = example["user_embed"].device
@@ -62,19 +67,19 @@ class GraphedLossStep:
             raise RuntimeError(msg)
         self.module = module
         self.device = device
-        self.static = {k: example[k].detach().clone() for k in _INPUT_KEYS}
-        self.static["user_embed"].requires_grad_(True)
-        self.static["item_embed"].requires_grad_(True)
-        self._staging = [{k: torch.empty_like(example[k]) for k in _INPUT_KEYS} for _ in range(2)]
-        self._uploaded = [torch.cuda.Event() for _ in range(2)]
-        self._consumed: list[torch.cuda.Event | None] = [None, None]
-        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        n = self.NUM_SLOTS
+        self._inputs = [{k: example[k].detach().clone() for k in _INPUT_KEYS} for _ in range(n)]
+        for slot in self._inputs:
+            slot["user_embed"].requires_grad_(True)
+            slot["item_embed"].requires_grad_(True)
+        self._uploaded = [torch.cuda.Event() for _ in range(n)]
+        self._consumed: list[torch.cuda.Event | None] = [None] * n
+        self._loss_host = torch.zeros(n, dtype=torch.float32).pin_memory()
         self._copy_stream = torch.cuda.Stream(device=device)
         self._next_slot = 0
-        self._pending: tuple[int, bool] | None = None
+        self._pending: int | None = None
 
-        def step() -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-            s = self.static
+        def step(s: dict[str, torch.Tensor]) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
             loss = module(s["user_embed"], s["item_embed"], s["target"], item_idx=s["item_idx"], pos_idx=s["pos_idx"])
             dq, dv = torch.autograd.grad(loss, (s["user_embed"], s["item_embed"]))
             return loss, dq, dv
@@ -83,29 +88,35 @@ class GraphedLossStep:
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                step()
+                step(self._inputs[0])
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.d_user, self.d_item = step()
+        self._graphs: list[torch.cuda.CUDAGraph] = []
+        self._outputs: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = []
+        pool = None
+        for slot in range(n):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=pool):
+                self._outputs.append(step(self._inputs[slot]))
+            pool = graph.pool()   # the graphs never run concurrently: they share one memory pool
+            self._graphs.append(graph)
         torch.cuda.synchronize(device)
 
     def prefetch(self, inputs: dict[str, torch.Tensor]) -> None:
-        """Start moving ``inputs`` into the next staging slot on the copy stream (returns at once)."""
+        """Start moving ``inputs`` into the next input slot on the copy stream (returns at once)."""
         if self._pending is not None:
             msg = "a prefetched step is already waiting: call submit() first"
             raise RuntimeError(msg)
         slot = self._next_slot
         consumed = self._consumed[slot]
-        with torch.cuda.stream(self._copy_stream):
+        with torch.cuda.stream(self._copy_stream), torch.no_grad():
             if consumed is not None:
-                self._copy_stream.wait_event(consumed)  # the step that last read this slot has taken its copy
+                self._copy_stream.wait_event(consumed)  # the step that last ran on this slot has finished
             for k in _INPUT_KEYS:
-                self._staging[slot][k].copy_(inputs[k], non_blocking=True)
+                self._inputs[slot][k].copy_(inputs[k], non_blocking=True)
             self._uploaded[slot].record(self._copy_stream)
-        self._pending = (slot, True)
-        self._next_slot = 1 - slot
+        self._pending = slot
+        self._next_slot = (slot + 1) % self.NUM_SLOTS
 
     def submit(self, inputs: dict[str, torch.Tensor] | None = None) -> StepResult:
         """Run one step on ``inputs`` (or on the inputs given to the last ``prefetch``); returns at once."""
@@ -114,18 +125,14 @@ class GraphedLossStep:
                 msg = "nothing to run: give inputs or call prefetch() first"
                 raise RuntimeError(msg)
             self.prefetch(inputs)
-        slot, _ = self._pending
+        slot = self._pending
         self._pending = None
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._uploaded[slot])
-        with torch.no_grad():
-            for k in _INPUT_KEYS:
-                self.static[k].copy_(self._staging[slot][k], non_blocking=True)
-        consumed = torch.cuda.Event()
-        consumed.record(cur)
-        self._consumed[slot] = consumed
-        self.graph.replay()
-        self._loss_host[slot : slot + 1].copy_(self.loss.detach().reshape(1), non_blocking=True)
+        self._graphs[slot].replay()
+        loss = self._outputs[slot][0]
+        self._loss_host[slot : slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         done = torch.cuda.Event()
         done.record(cur)
+        self._consumed[slot] = done   # the graph reads the slot's tensors throughout the step
         return StepResult(self, slot, done)
