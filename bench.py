@@ -654,8 +654,9 @@ def main() -> None:  # noqa: PLR0915
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "eager_blocking_value": e2e_eager_value, "h2d_only_GBps": h2d_gbps,
                 "pipeline": ("eager module calls; the pinned-host upload of step i+1 runs on a copy stream under step i" if args.no_graph else
-                             "xfmr_b200.GraphedLossStep: CUDA-graph replay; the pinned-host upload of step i+1 runs on a copy stream "
-                             "under step i and the loss of step i-1 is read on the host while step i runs")},
+                             "xfmr_b200.GraphedLossStep: CUDA-graph replay (one graph per input slot, no staging copy); the pinned-host "
+                             "upload of step i+1 runs on a copy stream under step i and the loss of step i-1 is read on the "
+                             "host while step i runs")},
         "gpu_launches": launches,
         "eager_ms_per_step": eager_ms,
         "roofline": {
