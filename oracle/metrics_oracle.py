@@ -7,7 +7,8 @@ here: **parity unpinned**; the functions restate torchmetrics' functional defini
 (``retrieval_normalized_dcg``, ``retrieval_recall``, ``retrieval_precision``, ``retrieval_average_precision``,
 ``retrieval_hit_rate``, ``retrieval_reciprocal_rank``) for a ranked list without score ties, with
 ``empty_target_action="neg"`` (a user without a relevant target scores 0) and the mean over users that
-``RetrievalMetric.compute`` takes.  Plain Python loops on purpose.
+``RetrievalMetric.compute`` takes.  Plain Python loops on purpose.  ``tests/test_oracle_extras.py`` checks hand-computed
+known answers and, for NDCG, scikit-learn's ``ndcg_score`` (same definition) on random cases.
 """
 
 from __future__ import annotations

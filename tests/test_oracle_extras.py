@@ -64,3 +64,32 @@ def test_new_workspace_queries_need_no_gpu() -> None:
                 _lib.UniformityDesc(n=64, dim=128, in_dtype=1, compute=0, t=0.0, reserved=0),
                 _lib.UniformityDesc(n=64, dim=512, in_dtype=1, compute=0, t=2.0, reserved=0)):
         assert _lib.lib.xb_uniformity_workspace_bytes(ctypes.byref(bad)) == 0
+
+
+def test_metric_oracle_ndcg_matches_scikit_learn() -> None:
+    """torchmetrics is not installable here; scikit-learn's ``ndcg_score`` (linear gain, log2 discount, top-k
+    truncation - the same definition) pins the NDCG column of the oracle on random cases."""
+    import numpy as np  # noqa: PLC0415
+
+    sklearn_metrics = pytest.importorskip("sklearn.metrics")
+    from oracle import metrics_oracle  # noqa: PLC0415
+
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n_docs = int(rng.integers(5, 40))
+        k = int(rng.integers(1, 12))
+        doc_ids = rng.permutation(1000)[:n_docs]
+        relevance = rng.integers(0, 6, n_docs).astype(float) * (rng.random(n_docs) < 0.5)
+        if relevance.sum() == 0:
+            relevance[0] = 3.0
+        scores = rng.standard_normal(n_docs)                       # distinct with probability 1: no ties
+        order = np.argsort(-scores)
+        ranked = doc_ids[order][:k].tolist()
+        targets = {int(d): float(r) for d, r in zip(doc_ids, relevance) if r > 0}
+        # documents that are not targets but are ranked count as irrelevant: the oracle sees them only in `ranked`
+        got = metrics_oracle.query_metrics(ranked, targets, k)
+        want = sklearn_metrics.ndcg_score(relevance[None, :], scores[None, :], k=k)
+        assert got[0] == pytest.approx(want, abs=1e-12)
+        hits = sum(1 for d in ranked if d in targets)
+        assert got[1] == pytest.approx(hits / len(targets))
+        assert got[2] == pytest.approx(hits / k)
