@@ -144,3 +144,36 @@ def test_reference_arm_prints_one_contract_line() -> None:
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+def test_exclusion_path_selection_and_padding_helpers() -> None:
+    """Host logic of ``ItemProcessor.search_batch``: dense bit mask while it is small, sparse post-filter otherwise,
+    a clear error when neither fits (no CUDA call is reached on these paths)."""
+    from xfmr_b200 import retrieval  # noqa: PLC0415
+
+    padded = retrieval.pad_id_lists([[3, 4], [], [5]])
+    assert padded.shape == (3, 2) and padded[1].tolist() == [retrieval._PAD_ID] * 2 and padded[2, 0] == 5  # noqa: SLF001
+    assert retrieval.pad_id_lists([[], []]).shape == (2, 1)                      # at least one column
+    vals = retrieval.pad_id_lists([[1.5], []], pad=0, dtype=torch.float32)
+    assert vals.dtype == torch.float32 and vals.tolist() == [[1.5], [0.0]]
+
+    index = xfmr_b200.ItemProcessor().get_index(torch.zeros(1000, 8), device="cpu")
+    assert index._exclusions(None, 4, 20) == (None, None)                        # noqa: SLF001
+    assert index._exclusions([[], [], [], []], 4, 20) == (None, None)            # noqa: SLF001
+    index.DENSE_MASK_BYTES = 0                                                   # force the sparse decision
+    mask, sparse = index._exclusions([[1, 2, 3], [4], [], [5, 6]], 4, 20)        # noqa: SLF001
+    assert mask is None and sparse.shape == (4, 3) and sparse[2].tolist() == [retrieval._PAD_ID] * 3  # noqa: SLF001
+    with pytest.raises(ValueError, match="one exclusion list per query"):
+        index._exclusions([[1]], 4, 20)                                          # noqa: SLF001
+    with pytest.raises(ValueError, match="exclusion lists of 250 ids"):
+        index._exclusions(torch.zeros(4, 250, dtype=torch.int64), 4, 20)         # noqa: SLF001
+    # metrics / filter / graph wrappers refuse CPU tensors like everything else
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.retrieval_metrics(torch.zeros(2, 3, dtype=torch.int64), torch.zeros(2, 1, dtype=torch.int64), torch.zeros(2, 1))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.topk_filter(torch.zeros(2, 5), torch.zeros(2, 5, dtype=torch.int64), torch.zeros(2, 1, dtype=torch.int64), 3)
+    inp = synthetic.make_loss_inputs(8, 16, 8, 2, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.GraphedLossStep(xfmr_b200.PairwiseHingeLoss(), inp)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        xfmr_b200.DirectAULoss()(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
