@@ -277,6 +277,7 @@ class ItemProcessor:
         self.embeddings: torch.Tensor | None = None
         self.item_ids: torch.Tensor | None = None
         self.item_text: Sequence[str] | None = None
+        self._row_of_id: dict[int, int] | None = None   # item id -> catalog row, built on the first text lookup
 
     def get_index(
         self,
@@ -295,6 +296,7 @@ class ItemProcessor:
         else:
             self.item_ids = torch.as_tensor(item_ids, dtype=torch.int64).to(device).contiguous()
         self.item_text = item_text
+        self._row_of_id = None
         return self
 
     def get_index_from_arrow(
@@ -479,7 +481,8 @@ class ItemProcessor:
             if self.item_ids is None:
                 rows = ids[keep].tolist()
             else:
-                lookup = {int(v): r for r, v in enumerate(self.item_ids.cpu().tolist())}
-                rows = [lookup[int(v)] for v in ids[keep].tolist()]
+                if self._row_of_id is None:   # once per index, not once per query
+                    self._row_of_id = {int(v): r for r, v in enumerate(self.item_ids.cpu().tolist())}
+                rows = [self._row_of_id[int(v)] for v in ids[keep].tolist()]
             frame[self.text_col] = [self.item_text[r] for r in rows]
         return pd.DataFrame(frame)

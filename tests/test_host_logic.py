@@ -177,3 +177,25 @@ def test_exclusion_path_selection_and_padding_helpers() -> None:
         xfmr_b200.GraphedLossStep(xfmr_b200.PairwiseHingeLoss(), inp)
     with pytest.raises(RuntimeError, match="no CPU path"):
         xfmr_b200.DirectAULoss()(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
+
+
+def test_search_frame_assembly_with_a_stubbed_kernel(monkeypatch) -> None:  # noqa: ANN001
+    """``ItemProcessor.search`` (data/lightning.py:237-259): result columns, empty slots dropped, text looked up by id.
+    The kernel call is stubbed: only the host-side assembly runs here."""
+    index = xfmr_b200.ItemProcessor(id_col="movie_id", text_col="movie_text").get_index(
+        torch.zeros(4, 8), torch.tensor([40, 10, 30, 20]), ["forty", "ten", "thirty", "twenty"], device="cpu")
+    calls = []
+
+    def fake_search_batch(embedding, exclude, top_k):  # noqa: ANN001, ANN202
+        calls.append((tuple(embedding.shape), exclude, top_k))
+        return torch.tensor([[0.9, 0.5, float("-inf")]]), torch.tensor([[30, 40, -1]])
+
+    monkeypatch.setattr(index, "search_batch", fake_search_batch)
+    frame = index.search(torch.zeros(8).numpy(), exclude_item_ids=[10], top_k=3)
+    assert calls == [((1, 8), [[10]], 3)]
+    assert list(frame.columns) == ["movie_id", "score", "movie_text"]
+    assert frame["movie_id"].tolist() == [30, 40] and frame["movie_text"].tolist() == ["thirty", "forty"]
+    assert frame["score"].tolist() == pytest.approx([0.9, 0.5])
+    frame2 = index.search(torch.zeros(1, 8).numpy(), None, top_k=3)            # no exclusions: None is passed through
+    assert calls[-1][1] is None and frame2["movie_text"].tolist() == ["thirty", "forty"]
+    assert index._row_of_id == {40: 0, 10: 1, 30: 2, 20: 3}                     # noqa: SLF001  built once, reused
