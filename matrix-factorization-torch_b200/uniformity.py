@@ -186,6 +186,7 @@ class MAWULoss(DirectAULoss):
     def forward(self, user_embed, item_embed, target, *, item_idx, pos_idx, log_q=None,  # noqa: ANN001, ANN201, PLR0913
                 user_margin=None, item_margin=None):  # noqa: ANN001
         self.check_inputs(user_embed, item_embed, target)
+        _lib.require_cuda(user_embed, item_embed, target, user_margin, item_margin)   # no CPU path, whatever the weights
         if user_margin is None and item_margin is None:
             align = self.alignment(user_embed, item_embed, target, item_idx=item_idx, pos_idx=pos_idx)
         else:

@@ -177,6 +177,10 @@ def test_exclusion_path_selection_and_padding_helpers() -> None:
         xfmr_b200.GraphedLossStep(xfmr_b200.PairwiseHingeLoss(), inp)
     with pytest.raises(RuntimeError, match="no CPU path"):
         xfmr_b200.DirectAULoss()(inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"])
+    with pytest.raises(RuntimeError, match="no CPU path"):   # even when only the torch-op margin term would be left
+        xfmr_b200.MAWULoss(gamma_user=0.0, gamma_item=0.0)(
+            inp["user_embed"], inp["item_embed"], inp["target"], item_idx=inp["item_idx"], pos_idx=inp["pos_idx"],
+            user_margin=torch.zeros(8), item_margin=torch.zeros(8))
 
 
 def test_search_frame_assembly_with_a_stubbed_kernel(monkeypatch) -> None:  # noqa: ANN001
