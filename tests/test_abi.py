@@ -73,3 +73,19 @@ def test_workspace_queries_need_no_gpu() -> None:
                              loss_mask=127, sigma=1.0, margin=1.0, has_log_q=0, mining=0)
     assert _lib.lib.xb_loss_workspace_bytes(ctypes.byref(too_wide)) == 0
     assert xfmr_b200._lib.lib.xb_mask_words(3706) == 4 * 29  # noqa: SLF001
+
+
+def test_header_is_plain_c() -> None:
+    """The boundary is a C ABI: the header must compile as C99 on its own (no C++ or torch types)."""
+    import shutil  # noqa: PLC0415
+    import tempfile  # noqa: PLC0415
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = ('#include "xfmr_b200.h"\n'
+           "int main(void) { xb_loss_desc d; xb_topk_desc t; xb_uniformity_desc u; d.mining = XB_MINING_HARD; t.k = 1; u.n = 2;\n"
+           "  (void)d; (void)t; (void)u; return XB_OK; }\n")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write(src)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(HEADER.parent), f.name],  # noqa: S603, S607
+                   check=True)
