@@ -19,6 +19,7 @@
 #include "../../include/xfmr_b200.h"
 #include "aux_kernels.cuh"
 #include "sweep_launch.h"
+#include "sweep_wg_launch.h"
 
 namespace xb {
 
@@ -233,6 +234,55 @@ static SweepPlan plan_sweep(int nR, int nC, int kp, int parts, bool has_g, bool 
 
 static inline int mask_words_for(int ncols) { return 4 * cdiv(ncols, BN); }
 
+// Launch plan of the warpgroup-per-tile sweep (sweep_wg.cuh): the n_rblocks x tb (row block, tile) pairs are cut into
+// `grid` equal runs of W pairs (stream-K), one CTA per SM at most.
+struct WgPlan {
+  int n_rblocks, tb, W, grid, pmax, nstages, nrbuf, nsb;
+  size_t smem;
+  bool ok;
+};
+static WgPlan plan_wg(int nR, int nC, int kp, int parts) {
+  WgPlan pl{};
+  pl.n_rblocks = cdiv(nR, BM);
+  pl.tb = cdiv(nC, BN);
+  pl.nsb = grad_bufs(kp);
+  const long long L = static_cast<long long>(pl.n_rblocks) * pl.tb;
+  pl.ok = false;
+  if (L <= 0 || L > (1ll << 30)) return pl;
+  int grid = L < NUM_SMS ? static_cast<int>(L) : NUM_SMS;
+  long long W = (L + grid - 1) / grid;
+  const long long w_min = L < 4 ? L : 4;          // a run shorter than a few tiles is all set-up
+  if (W < w_min) W = w_min;
+  pl.W = static_cast<int>(W);
+  pl.grid = static_cast<int>((L + W - 1) / W);
+  pl.pmax = wg_pmax(pl.tb, pl.W);
+  // shared memory: a ring of at least NSB + 1 column tiles (the score MMAs run NSB tiles ahead of the second MMAs);
+  // what is left takes a second row-tile buffer (the next segment's row tile loads under the current one) when the
+  // run holds several segments, more stages otherwise
+  const bool many_segments = pl.W > pl.tb;
+  for (int nr = many_segments ? 2 : 1; nr >= 1 && !pl.ok; --nr) {
+    for (int ns = WG_MAX_STAGES; ns >= (nr == 2 ? pl.nsb + 1 : 2); --ns) {
+      const WgSmemLayout lay = wg_smem_layout(kp, parts, ns, nr);
+      if (lay.total <= SMEM_BUDGET) {
+        pl.nstages = ns;
+        pl.nrbuf = nr;
+        pl.smem = lay.total;
+        pl.ok = true;
+        break;
+      }
+    }
+  }
+  return pl;
+}
+// XB_WG=0 keeps the single-loss training sweeps on the 16-warps-per-tile kernel of sweep.cuh
+static bool wg_enabled() {
+  static const bool enabled = [] {
+    const char* e = std::getenv("XB_WG");
+    return e == nullptr || e[0] != '0';
+  }();
+  return enabled;
+}
+
 // Single-loss calls run the forward statistics and the query-side gradient in ONE sweep (MODE_FWDQ).  For the
 // exponential losses the two separate sweeps stay behind as a device-side fallback (their per-row exponent reference
 // can overflow); the step / logistic losses have nothing to normalise and need none.  XB_MERGE_FWDQ=0 turns it off.
@@ -341,6 +391,8 @@ struct LossWs {
   int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
   bool mining;
   SweepPlan fwd, fq, gq, gi;   // forward / mining sweep, merged forward + dQ sweep, dQ sweep, dI sweep
+  WgPlan wq, wi;               // warpgroup-per-tile variants of the merged sweep and of the dI sweep (single-loss calls)
+  bool use_wg;
   size_t qprep, iprep, qaug, iaug, qn2, in2, qfwd, qmine, rowinfo, diag, ipar, mask, mask_t, pm_ws, part, rowstat, rowloss,
       ueff, flag, qg, qs, qaugb, csign, kvec, accq, rsq, acci, rsi, gdiag, cand, cand_cnt, sel, selcol, selL2, redpart, total;
 };
@@ -362,6 +414,9 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->gq = plan_sweep(B, N, w->kp, w->parts, true, true, 2);
   w->fq = plan_sweep(B, N, w->kp, w->parts, true, true, 6);
   w->gi = plan_sweep(N, B, w->kp, w->parts, true, true, gq_floats);
+  w->wq = plan_wg(B, N, w->kp, w->parts);
+  w->wi = plan_wg(N, B, w->kp, w->parts);
+  w->use_wg = wg_enabled() && !w->mining && lm != 0 && lm_single(lm) && w->wq.ok && w->wi.ok;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -383,7 +438,11 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->mask = take(sizeof(uint32_t) * w->B_pad * static_cast<size_t>(w->words));
   w->mask_t = take(sizeof(uint32_t) * w->N_pad * static_cast<size_t>(w->words_t));
   w->pm_ws = take(pair_mask_ws(N).total);
-  w->part = take(sizeof(float) * 8 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
+  {
+    size_t subs = static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS;
+    if (w->use_wg && static_cast<size_t>(w->wq.pmax) * WG_SUBS > subs) subs = static_cast<size_t>(w->wq.pmax) * WG_SUBS;
+    w->part = take(sizeof(float) * 8 * subs * w->B_pad);
+  }
   w->rowstat = take(sizeof(float4) * B);
   w->rowloss = take(sizeof(float) * 7 * B);
   w->ueff = take(sizeof(float) * 8);
@@ -395,7 +454,11 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->qaugb = take(static_cast<size_t>(AUG_COLS) * 2 * B);
   w->csign = take(sizeof(uint32_t) * (cdiv(B, 32) + 4));
   w->kvec = take(sizeof(float) * (w->B_pad + 4));   // |k_j| per query (+ the upstream sign behind it)
-  const int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
+  int nq = w->mining ? 1 : w->gq.nchunks, ni = w->mining ? 1 : w->gi.nchunks;
+  if (w->use_wg) {
+    if (w->wq.pmax > nq) nq = w->wq.pmax;
+    if (w->wi.pmax > ni) ni = w->wi.pmax;
+  }
   w->accq = take(sizeof(float) * static_cast<size_t>(nq) * w->B_pad * w->kp);
   w->rsq = take(sizeof(float) * 2 * static_cast<size_t>(nq) * MAX_EPI_PARTS * w->B_pad);
   w->acci = take(sizeof(float) * static_cast<size_t>(ni) * w->N_pad * w->kp);
@@ -487,6 +550,7 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   float* gdiag = reinterpret_cast<float*>(ws + w.gdiag);
   int nq = 1, ni = 1, nq_sub = 1, ni_sub = 1;
   int n_final_rows = N;   // item rows finished by grad_finalize_i_kernel (the rest are written by the dI sweep itself)
+  bool wg_items = false;  // the dI sweep ran warpgroup-per-tile
   const float* fq_part = nullptr;
   const float* fq_qg = nullptr;
   const int* fq_flag = nullptr;
@@ -568,6 +632,21 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
         p.csign = csign;
         p.kvec = kvec;
       }
+      if (w.use_wg) {
+        // warpgroup-per-tile kernel, stream-K runs (sweep_wg.cuh): row blocks that lie inside one CTA's run are written
+        // by the sweep itself, the in-batch blocks and the blocks cut by a run boundary go through partials
+        WgParams wp{};
+        wp.nR = N; wp.nC = B; wp.nR_pad = w.N_pad; wp.kp = w.kp; wp.parts = w.parts; wp.nstages = w.wi.nstages; wp.nrbuf = w.wi.nrbuf;
+        wp.n_ctiles = w.wi.tb; wp.n_rblocks = w.wi.n_rblocks; wp.W = w.wi.W;
+        wp.rpar = p.rpar; wp.cpar = nullptr; wp.mask = p.mask; wp.mask_words = p.mask_words;
+        wp.out_acc = acci; wp.out_rs = rsi;
+        wp.cabs = p.cabs; wp.gsign_src = p.gsign_src; wp.csign = p.csign; wp.kvec = p.kvec;
+        wp.out_final = di; wp.final_v = iprep; wp.final_rb0 = w.B_pad / BM; wp.final_d = d;
+        wp.final_dtype = sizeof(T) == 2 ? 1 : 0;
+        wp.trace = g_trace.load(); wp.trace_tiles = g_trace_tiles.load();
+        XB_SWEEP(launch_wg_gradi(lm, desc->has_log_q != 0, tmI, *tmQc, tmIa, *tmQca, wp, w.wi.grid, w.wi.smem, st));
+        wg_items = true;
+      } else {
       if (w.gi.nchunks == 1) {
         // one column chunk: item rows beyond the in-batch block get their gradient straight from the sweep
         p.out_final = di;
@@ -589,15 +668,22 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
                                      w.gi.smem, st));
       ni = w.gi.nchunks;
       ni_sub = ni * epi_parts(MODE_GRAD, lm, false);
+      }
     }
   }
   grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
       B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
-      dq, gdiag, fq_part, fq_qg, fq_flag, lm);
+      dq, gdiag, fq_part, fq_qg, fq_flag, lm, w.use_wg ? w.wq.tb : 0, w.use_wg ? w.wq.W : 0, w.use_wg ? WG_SUBS : 0);
   XB_LAUNCHED();
   if (skip_items) return XB_OK;   // (uniformity: the column-side gradient equals the row-side one)
-  grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(n_final_rows) * 32, 256), 256, 0, st>>>(
-      n_final_rows, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
+  if (wg_items) {
+    const long long vrows = static_cast<long long>(w.B_pad / BM + w.wi.grid - 1) * BM;
+    grad_finalize_i_kernel<T><<<cdiv(vrows * 32, 256), 256, 0, st>>>(N, B, d, w.kp, w.parts, w.N_pad, 1, 1, acci, rsi, iprep, qprep,
+                                                                    gdiag, di, w.wi.tb, w.wi.W, w.B_pad / BM);
+  } else {
+    grad_finalize_i_kernel<T><<<cdiv(static_cast<long long>(n_final_rows) * 32, 256), 256, 0, st>>>(
+        n_final_rows, B, d, w.kp, w.parts, w.N_pad, ni, ni_sub, acci, rsi, iprep, qprep, gdiag, di);
+  }
   XB_LAUNCHED();
   return XB_OK;
 }
@@ -757,6 +843,22 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         pq.mask_words = p.mask_words;
         pq.out_stats = p.out_stats;
         pq.out_acc = reinterpret_cast<float*>(ws + w.accq);
+        if (w.use_wg) {
+          // warpgroup-per-tile kernel, stream-K runs (sweep_wg.cuh)
+          WgParams wp{};
+          wp.nR = B; wp.nC = N; wp.nR_pad = w.B_pad; wp.kp = w.kp; wp.parts = w.parts; wp.nstages = w.wq.nstages; wp.nrbuf = w.wq.nrbuf;
+          wp.n_ctiles = w.wq.tb; wp.n_rblocks = w.wq.n_rblocks; wp.W = w.wq.W;
+          wp.rpar = p.rpar; wp.cpar = p.cpar; wp.mask = p.mask; wp.mask_words = p.mask_words;
+          wp.out_stats = p.out_stats;
+          wp.out_acc = reinterpret_cast<float*>(ws + w.accq);
+          wp.trace = g_trace.load(); wp.trace_tiles = g_trace_tiles.load();
+          XB_SWEEP(launch_wg_fwdq(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, wp, w.wq.grid, w.wq.smem, st));
+          loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+              B, p.nR_pad, w.wq.pmax * WG_SUBS, p.out_stats, desc->sigma, reinterpret_cast<float4*>(ws + w.rowinfo),
+              reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, grad_expfast(lm) ? flag : nullptr, nullptr, w.wq.tb,
+              w.wq.W, WG_SUBS);
+          XB_LAUNCHED();
+        } else {
         XB_SWEEP(launch_sweep_fwdq(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, pq, dim3(w.fq.nchunks, w.fq.n_rblocks),
                                    w.fq.smem, st));
         loss_rows_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(B, p.nR_pad, w.fq.nchunks * epi_parts(MODE_FWDQ, lm, true), p.out_stats, desc->sigma,
@@ -764,6 +866,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                                        reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss,
                                                        grad_expfast(lm) ? flag : nullptr, nullptr);
         XB_LAUNCHED();
+        }
         p.cond = flag;
       }
       if (!merged || grad_expfast(lm)) {   // the plain forward sweep: the only path, or the exponential losses' fallback

@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "sweep.cuh"
+#include "sweep_wg.cuh"
 
 namespace xb {
 
@@ -364,12 +365,14 @@ __device__ __forceinline__ void write_row_losses(int row, int B, float sigma, co
 __global__ void loss_rows_kernel(int B, int nR_pad, int nchunks, const float* __restrict__ part, float sigma,
                                  const float4* __restrict__ rowinfo, const float* __restrict__ diag,
                                  float4* __restrict__ rowstat, float* __restrict__ rowloss, int* __restrict__ flag_out,
-                                 const int* __restrict__ cond) {
+                                 const int* __restrict__ cond, int wg_tb = 0, int wg_w = 0, int wg_ep = 0) {
   if (cond != nullptr && *cond == 0) return;
   // one warp per row: lanes take the sub-chunks round-robin, then the (max, sum) pairs merge by shuffles
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
+  // statistics of the warpgroup-per-tile sweep (sweep_wg.cuh): the row block's pieces x warpgroups are valid, no more
+  if (wg_w > 0) nchunks = wg_pieces(row / BM, wg_tb, wg_w) * wg_ep;
   float cnt = 0.f, csum = 0.f, hsum = 0.f, lsum = 0.f, mx = NEG_BIG, se = 0.f;
   bool bad = false;
   for (int c = lane; c < nchunks; c += 32) {
@@ -642,10 +645,16 @@ __global__ void grad_finalize_q_kernel(int B, int d, int kp, int parts, int nR_p
                                        const float4* __restrict__ rowinfo, const float4* __restrict__ rowstat,
                                        T* __restrict__ dq, float* __restrict__ gdiag,
                                        const float* __restrict__ fq_part, const float* __restrict__ fq_qg,
-                                       const int* __restrict__ fq_flag, int lm) {
+                                       const int* __restrict__ fq_flag, int lm, int wg_tb = 0, int wg_w = 0,
+                                       int wg_ep = 0) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
+  if (wg_w > 0 && fq_part != nullptr && *fq_flag == 0) {
+    // the merged sweep ran warpgroup-per-tile (sweep_wg.cuh): one partial per piece of the row block
+    nchunks = wg_pieces(row / BM, wg_tb, wg_w);
+    nsub = nchunks * wg_ep;
+  }
   // Merged forward + dQ sweep (MODE_FWDQ, fq_part != nullptr and no fallback).  Exponential losses: chunk c holds
   // acc_c = sum_j 2^(x_ij - m_ic) v_j and its column parts se_icp = sum_j 2^(x_ij - m_ic); with G_ij = k_i 2^(x_ij +
   // off_i) both scale by f_ic = k_i 2^(m_ic + off_i).  Step / logistic losses: acc_c = sum_j G'_ij v_j, se = sum_j G'_ij
@@ -738,9 +747,26 @@ template <typename T>
 __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, int nR_pad, int nchunks, int nsub,
                                        const float* __restrict__ acc, const float* __restrict__ rs_part,
                                        const __nv_bfloat16* __restrict__ ip, const __nv_bfloat16* __restrict__ qp,
-                                       const float* __restrict__ gdiag, T* __restrict__ di) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                       const float* __restrict__ gdiag, T* __restrict__ di, int wg_tb = 0,
+                                       int wg_w = 0, int wg_rb0 = 0) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (wg_w > 0) {
+    // warpgroup-per-tile sweep (sweep_wg.cuh): it wrote the row blocks at or beyond wg_rb0 that lie inside one CTA's run
+    // itself; left are the in-batch row blocks [0, wg_rb0) and the row blocks cut by a run boundary c * W.  The grid
+    // covers wg_rb0 + (#CTAs - 1) virtual blocks of BM rows.
+    const int v = row / BM;
+    int rb = v;
+    if (v >= wg_rb0) {
+      const long long lin = static_cast<long long>(v - wg_rb0 + 1) * wg_w;
+      rb = static_cast<int>(lin / wg_tb);
+      if (lin % wg_tb == 0 || rb < wg_rb0) return;                                   // no cut here / already covered
+      if (static_cast<long long>(v - wg_rb0) * wg_w > static_cast<long long>(rb) * wg_tb) return;   // an earlier cut owns this block
+    }
+    row = rb * BM + (row - v * BM);
+    if (row >= N) return;
+    nchunks = nsub = wg_pieces(rb, wg_tb, wg_w);
+  }
   if (row >= N) return;
   float cg = 0.f;
   for (int c = 0; c < nsub; ++c) cg += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
