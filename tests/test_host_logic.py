@@ -127,23 +127,38 @@ def test_arrow_catalog_adapter_reads_the_reference_table_layout(tmp_path) -> Non
 
 
 def test_reference_arm_prints_one_contract_line() -> None:
-    """``bench.py --impl reference``: the CPU port timed on the host cores, one JSON line with the contract keys."""
+    """``bench.py --impl reference``: the reference's side timed on the host cores, one JSON line with the contract keys,
+    the requested steps honoured, measured (not extrapolated) milliseconds, and the product library never mapped."""
     import json  # noqa: PLC0415
     import pathlib  # noqa: PLC0415
     import subprocess  # noqa: PLC0415
     import sys  # noqa: PLC0415
 
     root = pathlib.Path(__file__).resolve().parents[1]
-    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],  # noqa: S603
-                         capture_output=True, text=True, check=True, timeout=600)
+    probe = (
+        "import runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '2', '--warmup', '1', '--no-extras'];"
+        "runpy.run_path(r'%s', run_name='__main__');"
+        "maps = open('/proc/self/maps').read(); sys.stderr.write('MAPPED_PRODUCT=%%d\\n' %% ('libxfmr_b200' in maps))"
+    ) % str(root / "bench.py")
+    out = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, check=True, timeout=900)  # noqa: S603
+    assert "MAPPED_PRODUCT=0" in out.stderr, "the reference arm must not load libxfmr_b200.so"
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     line = json.loads(lines[0])
-    assert line["impl"] == "reference" and line["metric"] == "fused_loss_fwd_bwd_samples_per_s" and line["unit"] == "samples/s"
+    assert line["impl"] == "reference" and line["metric"] == "exact_top100_retrieval_queries_per_s" and line["unit"] == "queries/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
-    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["ms_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["vs_baseline"] is None
+    # both arms print the same config object
+    import importlib.util  # noqa: PLC0415
+
+    spec = importlib.util.spec_from_file_location("xb_bench", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert line["config"] == bench.workload_config(bench.C5["num_items"], bench.C5["num_queries"])
 
 
 def test_exclusion_path_selection_and_padding_helpers() -> None:
