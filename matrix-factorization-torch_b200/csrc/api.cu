@@ -1053,12 +1053,27 @@ namespace {
 struct TopkWs {
   int kp, parts, Q_pad, cap, kfetch;
   SweepPlan plan;
+  // retrieval kernel of sweep_rt.cuh (bf16 operands, dim <= 128): stream-K runs over (query-tile pair, item tile)
+  bool use_rt;
+  int rt_pairs, rt_W, rt_grid, rt_pmax, rt_stages, rt_tc, rt_chunks;
+  size_t cand_thr;
+  size_t rt_smem;
   size_t qprep, iprep, cand, cand_cnt, ent, scores, ids, total;
   bool items_inplace;  // the caller's bf16 catalog already has the prepared layout
 };
 int topk_cap_for(int kfetch) {
+  // candidate buffer per (row, stream): room for the kept entries (kfetch + a quarter of slack, see compact_select) and
+  // at least 48 new ones.  Small buffers mean frequent compactions but FRESH admission thresholds: at k' = 132 a
+  // 256-entry buffer admits ~1.6 x the items a 512-entry one does between compactions... measured 246.7 vs 242.2 k
+  // queries/s on a 12.5 M-item shard.  XB_TOPK_CAP forces a size.
+  static const int forced = [] {
+    const char* e = std::getenv("XB_TOPK_CAP");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  const int need = kfetch + kfetch / 4 + 48;
   int cap = 64;
-  while (cap < 2 * kfetch + 32) cap <<= 1;
+  while (cap < need) cap <<= 1;
+  if (forced >= cap && forced <= 1024 && (forced & (forced - 1)) == 0) return forced;
   return cap;
 }
 bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
@@ -1072,6 +1087,53 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   w->cap = topk_cap_for(w->kfetch);
   w->plan = plan_sweep(d->num_queries, d->num_items, w->kp, w->parts, false, false, 2, 4 * epi_parts(MODE_TOPK, 0, true));
   w->items_inplace = (d->in_dtype == XB_DTYPE_BF16 && w->parts == 1 && d->dim == w->kp);
+  w->use_rt = false;
+  {
+    static const bool rt_enabled = [] {
+      const char* e = std::getenv("XB_RT");
+      return e == nullptr || e[0] != '0';
+    }();
+    const long long tb = cdiv(d->num_items, BN);
+    w->rt_pairs = cdiv(cdiv(d->num_queries, BM), 2);
+    // the catalog is swept in chunks that stay L2 resident while every CTA passes over them (64 MB of bf16 rows)
+    static const long long chunk_mb = [] {
+      const char* e = std::getenv("XB_RT_CHUNK_MB");
+      const long long v = e != nullptr ? atoll(e) : 0;
+      return v > 0 ? v : 64ll;
+    }();
+    const long long tc_max = (chunk_mb << 20) / (static_cast<long long>(w->kp) * 2 * BN);
+    const long long tc = tb < tc_max ? tb : tc_max;
+    w->rt_tc = static_cast<int>(tc > 0 ? tc : 1);
+    w->rt_chunks = static_cast<int>((tb + w->rt_tc - 1) / w->rt_tc);
+    const long long L = static_cast<long long>(w->rt_pairs) * w->rt_tc;
+    if (rt_enabled && w->parts == 1 && w->kp <= 128 && L > 0 && L < (1ll << 30) && tb < (1ll << 30)) {
+      int grid = L < NUM_SMS ? static_cast<int>(L) : NUM_SMS;
+      long long W = (L + grid - 1) / grid;
+      const long long w_min = L < 16 ? L : 16;      // a run shorter than a few tiles is all set-up
+      if (W < w_min) W = w_min;
+      // More pairs than SMs: runs end on pair boundaries (W a multiple of Tc), e.g. 128 CTAs x 2 pairs at config 5.  A
+      // pair cut in two becomes two candidate streams that each collect their own top k' (measured at a 12.5 M-item
+      // shard: 403 streams on 148 CTAs 266 ms, 256 streams on 128 CTAs 235 ms; at 100 M items the two are equal: the
+      // 20 idle SMs go into higher clocks under the power cap).  XB_RT_WHOLE=0 restores the even cut.
+      static const bool whole = [] {
+        const char* e = std::getenv("XB_RT_WHOLE");
+        return e == nullptr || e[0] != '0';
+      }();
+      if (whole && W > w->rt_tc) W = (W + w->rt_tc - 1) / w->rt_tc * w->rt_tc;
+      w->rt_W = static_cast<int>(W);
+      w->rt_grid = static_cast<int>((L + W - 1) / W);
+      w->rt_pmax = wg_pmax(w->rt_tc, w->rt_W);
+      for (int ns = RT_MAX_STAGES; ns >= 2; --ns) {
+        const RtSmemLayout lay = rt_smem_layout(w->kp, ns);
+        if (lay.total <= SMEM_BUDGET) {
+          w->rt_stages = ns;
+          w->rt_smem = lay.total;
+          w->use_rt = true;
+          break;
+        }
+      }
+    }
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -1081,8 +1143,11 @@ bool topk_ws_layout(const xb_topk_desc* d, TopkWs* w) {
   const size_t rowb = static_cast<size_t>(w->parts) * w->kp * 2;
   w->qprep = take(rowb * d->num_queries);
   w->iprep = take(w->items_inplace ? 0 : rowb * static_cast<size_t>(d->num_items));
-  w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->plan.nchunks) * MAX_EPI_PARTS * w->Q_pad * w->cap);
-  w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->plan.nchunks) * MAX_EPI_PARTS * w->Q_pad);
+  size_t streams = static_cast<size_t>(w->plan.nchunks) * MAX_EPI_PARTS;
+  if (w->use_rt && static_cast<size_t>(w->rt_pmax) * RT_HALVES > streams) streams = static_cast<size_t>(w->rt_pmax) * RT_HALVES;
+  w->cand = take(sizeof(unsigned long long) * streams * w->Q_pad * w->cap);
+  w->cand_cnt = take(sizeof(int) * streams * w->Q_pad);
+  w->cand_thr = take(sizeof(float) * streams * w->Q_pad);
   w->ent = take(sizeof(unsigned long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->scores = take(sizeof(float) * static_cast<size_t>(d->num_queries) * w->kfetch);
   w->ids = take(sizeof(long long) * static_cast<size_t>(d->num_queries) * w->kfetch);
@@ -1146,10 +1211,23 @@ int xb_topk_search(const xb_topk_desc* desc, const void* queries, const void* it
   p.cap = w.cap;
   p.keep = w.kfetch;
   p.topk_mining = 0;
-  XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(ws + w.ent);
-  cand_finalize_kernel<<<cdiv(Q, 4), 128, 0, st>>>(
-      Q, p.nR_pad, w.plan.nchunks * epi_parts(MODE_TOPK, 0, true), w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
+  if (w.use_rt) {
+    RtParams rp{};
+    rp.nR = Q; rp.nC = N; rp.nR_pad = w.Q_pad; rp.kp = w.kp; rp.nstages = w.rt_stages;
+    rp.n_ctiles = cdiv(N, BN); rp.n_rpairs = w.rt_pairs; rp.W = w.rt_W; rp.chunk_tiles = w.rt_tc; rp.n_chunks = w.rt_chunks;
+    rp.cand_thr = reinterpret_cast<float*>(ws + w.cand_thr);
+    rp.mask = p.mask; rp.mask_words = p.mask_words;
+    rp.cand = p.cand; rp.cand_cnt = p.cand_cnt; rp.cap = w.cap; rp.keep = w.kfetch;
+    const int nsub = w.rt_pmax * RT_HALVES;
+    XB_CUDA(cudaMemsetAsync(rp.cand_cnt, 0, sizeof(int) * static_cast<size_t>(nsub) * w.Q_pad, st));   // unused pieces stay empty
+    XB_SWEEP(launch_rt(tmQ, tmI, rp, w.rt_grid, w.rt_smem, st));
+    cand_finalize_kernel<<<cdiv(Q, 4), 128, 0, st>>>(Q, w.Q_pad, nsub, w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
+  } else {
+    XB_SWEEP(launch_sweep_topk(false, tmQ, tmI, tmQ, tmI, p, dim3(w.plan.nchunks, w.plan.n_rblocks), w.plan.smem, st));
+    cand_finalize_kernel<<<cdiv(Q, 4), 128, 0, st>>>(
+        Q, p.nR_pad, w.plan.nchunks * epi_parts(MODE_TOPK, 0, true), w.cap, w.kfetch, p.cand, p.cand_cnt, ent, w.kfetch, 0);
+  }
   XB_LAUNCHED();
   float* stmp = reinterpret_cast<float*>(ws + w.scores);
   long long* itmp = reinterpret_cast<long long*>(ws + w.ids);

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "sweep_rt.cuh"
 #include "sweep_wg.cuh"
 
 namespace xb {
@@ -10,6 +11,8 @@ cudaError_t launch_wg_fwdq(int lm, bool logq, const CUtensorMap& tmR, const CUte
                            const WgParams& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_wg_gradi(int lm, bool logq, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
                             const WgParams& p, int grid, size_t smem, cudaStream_t st);
+
+cudaError_t launch_rt(const CUtensorMap& tmR, const CUtensorMap& tmC, const RtParams& p, int grid, size_t smem, cudaStream_t st);
 
 template <typename K>
 inline cudaError_t launch_wg_impl(K kernel, const CUtensorMap& tmR, const CUtensorMap& tmC, const CUtensorMap& tmRa, const CUtensorMap& tmCa,
