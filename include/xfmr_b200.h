@@ -16,7 +16,13 @@
  *   - all work is ordered on `stream` (a cudaStream_t passed as void*); no host synchronisation, no
  *     default-stream use, no memory allocation: calls are CUDA-graph capturable.  xb_loss_forward runs its
  *     mask builder on a library-owned helper stream that forks from `stream` and joins back into it with
- *     events before the call returns to it (XB_FORK=0 keeps everything on `stream`);
+ *     events before the call returns to it, also on every error return (XB_FORK=0 keeps everything on `stream`);
+ *   - Threading: entry points are re-entrant; any number of host threads may call them concurrently on the same
+ *     or different devices / streams.  The helper stream and its events are per host thread and device, so a
+ *     thread that is capturing a CUDA graph pulls only its own helper stream into the capture and never sees
+ *     work enqueued by another thread.  A workspace belongs to one call sequence (forward, then its backward)
+ *     at a time; xb_last_error_string() and the debug / timing hooks (xb_debug_*, xb_sweep_timing*) are the
+ *     only per-thread / process-wide state;
  *   - return value: 0 = ok, < 0 = error code below; xb_last_error_string() describes the last failure on
  *     the calling thread.  Nothing throws or aborts across the ABI;
  *   - there is no CPU path: a build without a GPU still loads, but every compute entry point needs sm_100.

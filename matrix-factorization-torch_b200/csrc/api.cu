@@ -80,25 +80,26 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
 static std::atomic<long long*> g_trace{nullptr};
 static std::atomic<int> g_trace_tiles{0};
 
-// A library-owned helper stream per device.  Independent pieces of one call (the false-negative mask builder vs the
+// A helper stream per device AND HOST THREAD.  Independent pieces of one call (the false-negative mask builder vs the
 // operand preparation) fork from the caller's stream and join back into it through events, so the call stays ordered
-// on - and capturable from - the caller's stream while its small latency-bound kernels overlap.  XB_FORK=0 disables it.
+// on - and capturable from - the caller's stream while its small latency-bound kernels overlap.  The lane is
+// thread-local: a host thread that is capturing a CUDA graph pulls only its own helper stream into the capture, and a
+// second thread issuing eager calls on the same device uses another one (include/xfmr_b200.h, "Threading").
+// XB_FORK=0 disables the fork.
 struct SideLane {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   bool tried = false, ok = false;
 };
-static std::mutex g_side_mutex;
-static SideLane g_side[64];
-static SideLane* side_lane() {
+static SideLane* side_lane(int which = 0) {
   static const bool enabled = [] {
     const char* e = std::getenv("XB_FORK");
     return e == nullptr || e[0] != '0';
   }();
+  thread_local SideLane lanes[64][2];
   int dev = -1;
   if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(g_side_mutex);
-  SideLane& l = g_side[dev];
+  SideLane& l = lanes[dev][which & 1];
   if (!l.tried) {
     l.tried = true;
     l.ok = cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) == cudaSuccess &&
@@ -108,16 +109,26 @@ static SideLane* side_lane() {
   }
   return l.ok ? &l : nullptr;
 }
-// fork: everything enqueued on `st` so far happens before what follows on the helper stream (record + wait are
-// issued under the lock so that two host threads cannot interleave their pairs)
+// fork: everything enqueued on `st` so far happens before what follows on the helper stream
 static bool side_fork(SideLane* l, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_side_mutex);
   return cudaEventRecord(l->fork, st) == cudaSuccess && cudaStreamWaitEvent(l->s, l->fork, 0) == cudaSuccess;
 }
 static bool side_join(SideLane* l, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_side_mutex);
   return cudaEventRecord(l->join, l->s) == cudaSuccess && cudaStreamWaitEvent(st, l->join, 0) == cudaSuccess;
 }
+// joins the lane back into the caller's stream on every way out of a scope (an un-joined helper stream would
+// invalidate an active capture)
+struct SideJoinGuard {
+  SideLane* lane;
+  cudaStream_t st;
+  bool joined = false;
+  bool join() {
+    if (lane == nullptr || joined) return true;
+    joined = true;
+    return side_join(lane, st);
+  }
+  ~SideJoinGuard() { (void)join(); }
+};
 
 static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -330,9 +341,11 @@ static PairMaskWs pair_mask_ws(int ncols) {
   return w;
 }
 
+// `init_lane` (optional): the two bit matrices are initialised on that helper stream beside the hash-table build and
+// joined before the marking kernel (they are independent until then: 20 us of stores beside 26 us of small kernels)
 static int build_pair_mask(int nrows, int ncols, int list_len, const long long* col_ids, const long long* row_ids0,
                            const long long* row_lists, uint32_t* mask, uint32_t* mask_t, uint8_t* ws,
-                           cudaStream_t st) {
+                           cudaStream_t st, SideLane* init_lane = nullptr) {
   const PairMaskWs w = pair_mask_ws(ncols);
   long long* keys = reinterpret_cast<long long*>(ws + w.keys_off);
   int* cnt = reinterpret_cast<int*>(ws + w.cnt_off);
@@ -343,16 +356,21 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
   int* cursor = reinterpret_cast<int*>(ws + w.cursor_off);
   const int words = mask_words_for(ncols), words_t = mask_words_for(nrows);
   const int rows_pad = cdiv(nrows, BM) * BM, cols_pad = cdiv(ncols, BM) * BM;
-  {
-    mask_init_kernel<<<cdiv(static_cast<long long>(rows_pad) * (words / 4), 256), 256, 0, st>>>(mask, rows_pad, words, nrows, ncols);
-    XB_LAUNCHED();
-  }
-  if (mask_t != nullptr) {
-    mask_init_kernel<<<cdiv(static_cast<long long>(cols_pad) * (words_t / 4), 256), 256, 0, st>>>(mask_t, cols_pad, words_t, ncols, nrows);
-    XB_LAUNCHED();
-  }
   const bool any_ids = (row_ids0 != nullptr) || (row_lists != nullptr && list_len > 0);
-  if (!any_ids || ncols == 0 || nrows == 0) return XB_OK;
+  const bool marks = any_ids && ncols != 0 && nrows != 0;
+  if (!marks) init_lane = nullptr;
+  if (init_lane != nullptr && !side_fork(init_lane, st)) return fail(XB_ERR_CUDA, "stream fork failed");
+  SideJoinGuard init_guard{init_lane, st};
+  {
+    cudaStream_t ist = init_lane != nullptr ? init_lane->s : st;
+    mask_init_kernel<<<cdiv(static_cast<long long>(rows_pad) * (words / 4), 256), 256, 0, ist>>>(mask, rows_pad, words, nrows, ncols);
+    XB_LAUNCHED();
+    if (mask_t != nullptr) {
+      mask_init_kernel<<<cdiv(static_cast<long long>(cols_pad) * (words_t / 4), 256), 256, 0, ist>>>(mask_t, cols_pad, words_t, ncols, nrows);
+      XB_LAUNCHED();
+    }
+  }
+  if (!marks) return XB_OK;
   hash_clear_kernel<<<cdiv(w.tsize, 256), 256, 0, st>>>(keys, cnt, fill, cursor, w.tsize);
   XB_LAUNCHED();
   hash_insert_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(col_ids, ncols, keys, cnt, slot_of, w.tsize - 1);
@@ -361,6 +379,7 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
   XB_LAUNCHED();
   hash_fill_kernel<<<cdiv(ncols, 256), 256, 0, st>>>(ncols, slot_of, start, fill, cols);
   XB_LAUNCHED();
+  if (!init_guard.join()) return fail(XB_ERR_CUDA, "stream join failed");
   const int ll = (row_lists != nullptr) ? list_len : 0;
   const long long threads = static_cast<long long>(nrows) * (ll + 1);
   hash_mark_kernel<<<cdiv(threads, 256), 256, 0, st>>>(nrows, ll, row_ids0, row_lists, keys, cnt, start, cols, w.tsize - 1,
@@ -536,8 +555,13 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   const int B = desc->batch, N = desc->num_items, d = desc->dim;
   const int lm = sweep_lm_from_mask(desc->loss_mask);
   float* ueff = reinterpret_cast<float*>(ws + w.ueff);
-  mask_upstream_kernel<<<1, 32, 0, st>>>(d_losses, desc->loss_mask, ueff);
-  XB_LAUNCHED();
+  // single-loss dense calls: one set-up launch (grad_prepare_kernel) instead of upstream masking, per-query
+  // coefficients, two memsets and the operand folding
+  const bool fused_prepare = lm != 0 && lm_single(lm) && !w.mining && !skip_items;
+  if (!fused_prepare) {
+    mask_upstream_kernel<<<1, 32, 0, st>>>(d_losses, desc->loss_mask, ueff);
+    XB_LAUNCHED();
+  }
   __nv_bfloat16* qprep = reinterpret_cast<__nv_bfloat16*>(ws + w.qprep);
   __nv_bfloat16* iprep = reinterpret_cast<__nv_bfloat16*>(ws + w.iprep);
   float4* qfwd = reinterpret_cast<float4*>(ws + w.qfwd);
@@ -549,11 +573,22 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   float* rsi = reinterpret_cast<float*>(ws + w.rsi);
   float* gdiag = reinterpret_cast<float*>(ws + w.gdiag);
   int nq = 1, ni = 1, nq_sub = 1, ni_sub = 1;
-  int n_final_rows = N;   // item rows finished by grad_finalize_i_kernel (the rest are written by the dI sweep itself)
-  bool wg_items = false;  // the dI sweep ran warpgroup-per-tile
+  SideLane* q_lane = nullptr;
+  SideJoinGuard q_guard{nullptr, st};
+  bool q_done = false;
   const float* fq_part = nullptr;
   const float* fq_qg = nullptr;
   const int* fq_flag = nullptr;
+  // dQ_i = sum_j G_ij v_j + diagonal terms (grad_finalize_q_kernel); also leaves G_ii in `gdiag` for the item side
+  auto finalize_q = [&](cudaStream_t qs) -> int {
+    grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, qs>>>(
+        B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
+        dq, gdiag, fq_part, fq_qg, fq_flag, lm, w.use_wg ? w.wq.tb : 0, w.use_wg ? w.wq.W : 0, w.use_wg ? WG_SUBS : 0);
+    XB_LAUNCHED();
+    return XB_OK;
+  };
+  int n_final_rows = N;   // item rows finished by grad_finalize_i_kernel (the rest are written by the dI sweep itself)
+  bool wg_items = false;  // the dI sweep ran warpgroup-per-tile
   if (lm == 0 || w.mining) {
     XB_CUDA(cudaMemsetAsync(accq, 0, sizeof(float) * static_cast<size_t>(w.B_pad) * w.kp, st));
     XB_CUDA(cudaMemsetAsync(rsq, 0, sizeof(float) * 2 * static_cast<size_t>(w.B_pad), st));
@@ -567,7 +602,17 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     }
   } else {
     float* qg = reinterpret_cast<float*>(ws + w.qg);
-    grad_params_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, lm, ueff, desc->sigma, qfwd, rowinfo, rowstat, qg);
+    float cabs = fabsf(desc->sigma) * 1.4426950408889634f;
+    if (!(cabs > 0.f)) cabs = 1.f;
+    if (fused_prepare) {
+      float* kvec = reinterpret_cast<float*>(ws + w.kvec);
+      grad_prepare_kernel<<<cdiv(static_cast<long long>(w.B_pad) * 32, 256), 256, 0, st>>>(
+          B, w.B_pad, w.kp, w.parts, lm, desc->loss_mask, d_losses, desc->sigma, qfwd, rowinfo, rowstat, qprep,
+          reinterpret_cast<const float*>(ws + w.qn2), cabs, ueff, qg, reinterpret_cast<__nv_bfloat16*>(ws + w.qs),
+          reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), reinterpret_cast<uint32_t*>(ws + w.csign), kvec, kvec + w.B_pad);
+    } else {
+      grad_params_kernel<<<cdiv(B, 128), 128, 0, st>>>(B, lm, ueff, desc->sigma, qfwd, rowinfo, rowstat, qg);
+    }
     XB_LAUNCHED();
     CUtensorMap tmQ, tmI, tmQa, tmIa;
     if ((rc = make_operand_map(&tmQ, ws + w.qprep, B, static_cast<long long>(w.parts) * w.kp))) return rc;
@@ -580,21 +625,35 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
     fq_part = merged ? reinterpret_cast<const float*>(ws + w.part) : nullptr;
     fq_qg = qg;
     fq_flag = flag;
-    if (!merged || grad_expfast(lm)) {  // dQ sweep: rows = queries, columns = items (merged forward: only as its fallback)
-      SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
-      p.use_aug = 1;
-      p.cond = merged ? flag : nullptr;
-      p.rpar = qg;
-      p.cpar = reinterpret_cast<float*>(ws + w.ipar);
-      p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
-      p.mask_words = w.words;
-      p.out_acc = accq;
-      p.out_stats = rsq;
-      XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
-                                     w.gq.smem, st));
-    }
     nq = w.gq.nchunks;
     nq_sub = nq * epi_parts(MODE_GRAD, lm, true);
+    // The query side - the dQ sweep (merged forward: only as its conditional fallback) and the dQ finalisation - depends
+    // on nothing the item-major sweep produces: it runs on the helper stream beside that sweep and joins before the
+    // item-side finalisation, which reads the diagonal terms it leaves in `gdiag`.
+    q_lane = skip_items ? nullptr : side_lane();
+    if (q_lane != nullptr && !side_fork(q_lane, st)) return fail(XB_ERR_CUDA, "stream fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+    q_guard.lane = q_lane;
+    {
+      cudaStream_t main_st = st;
+      cudaStream_t st = q_lane != nullptr ? q_lane->s : main_st;   // (XB_SWEEP records its events on `st`)
+      if (!merged || grad_expfast(lm)) {  // dQ sweep: rows = queries, columns = items
+        SweepParams p = base_params(B, N, w.kp, w.parts, w.gq);
+        p.use_aug = 1;
+        p.cond = merged ? flag : nullptr;
+        p.rpar = qg;
+        p.cpar = reinterpret_cast<float*>(ws + w.ipar);
+        p.mask = reinterpret_cast<uint32_t*>(ws + w.mask);
+        p.mask_words = w.words;
+        p.out_acc = accq;
+        p.out_stats = rsq;
+        XB_SWEEP(launch_sweep_grad_qrow(lm, desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, dim3(w.gq.nchunks, w.gq.n_rblocks),
+                                       w.gq.smem, st));
+      }
+      if (q_lane != nullptr) {
+        if ((rc = finalize_q(st)) != XB_OK) return rc;
+        q_done = true;
+      }
+    }
     if (!skip_items) {  // dI sweep: rows = items, columns = queries (transposed mask)
       SweepParams p = base_params(N, B, w.kp, w.parts, w.gi);
       p.use_aug = 1;
@@ -610,19 +669,19 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       if (lm_single(lm)) {
         // exponential loss: fold sign, offset and magnitude of every query into the streamed operand and its aug
         // block, so the epilogue of the item-major sweep needs no per-column parameters
-        float cabs = fabsf(desc->sigma) * 1.4426950408889634f;
-        if (!(cabs > 0.f)) cabs = 1.f;
         uint32_t* csign = reinterpret_cast<uint32_t*>(ws + w.csign);
-        if (cudaMemsetAsync(csign, 0, sizeof(uint32_t) * (cdiv(B, 32) + 4), st) != cudaSuccess)
-          return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
         float* kvec = reinterpret_cast<float*>(ws + w.kvec);
-        if (cudaMemsetAsync(kvec, 0, sizeof(float) * (w.B_pad + 4), st) != cudaSuccess)
-          return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
-        grad_fold_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
-            B, w.kp, w.parts, lm, qprep, reinterpret_cast<const float*>(ws + w.qn2), qg, cabs, ueff,
-            reinterpret_cast<__nv_bfloat16*>(ws + w.qs), reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), csign, kvec,
-            kvec + w.B_pad);
-        XB_LAUNCHED();
+        if (!fused_prepare) {
+          if (cudaMemsetAsync(csign, 0, sizeof(uint32_t) * (cdiv(B, 32) + 4), st) != cudaSuccess)
+            return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
+          if (cudaMemsetAsync(kvec, 0, sizeof(float) * (w.B_pad + 4), st) != cudaSuccess)
+            return fail(XB_ERR_CUDA, "cudaMemsetAsync failed");
+          grad_fold_kernel<<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
+              B, w.kp, w.parts, lm, qprep, reinterpret_cast<const float*>(ws + w.qn2), qg, cabs, ueff,
+              reinterpret_cast<__nv_bfloat16*>(ws + w.qs), reinterpret_cast<__nv_bfloat16*>(ws + w.qaugb), csign, kvec,
+              kvec + w.B_pad);
+          XB_LAUNCHED();
+        }
         if ((rc = make_operand_map(&tmQs, ws + w.qs, B, static_cast<long long>(w.parts) * w.kp))) return rc;
         if ((rc = make_aug_map(&tmQab, ws + w.qaugb, B))) return rc;
         tmQc = &tmQs;
@@ -671,11 +730,9 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
       }
     }
   }
-  grad_finalize_q_kernel<T><<<cdiv(static_cast<long long>(B) * 32, 256), 256, 0, st>>>(
-      B, d, w.kp, w.parts, w.B_pad, nq, nq_sub, accq, rsq, qprep, iprep, ueff, desc->sigma, desc->loss_mask, rowinfo, rowstat,
-      dq, gdiag, fq_part, fq_qg, fq_flag, lm, w.use_wg ? w.wq.tb : 0, w.use_wg ? w.wq.W : 0, w.use_wg ? WG_SUBS : 0);
-  XB_LAUNCHED();
+  if (!q_done && (rc = finalize_q(st)) != XB_OK) return rc;
   if (skip_items) return XB_OK;   // (uniformity: the column-side gradient equals the row-side one)
+  if (!q_guard.join()) return fail(XB_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (wg_items) {
     const long long vrows = static_cast<long long>(w.B_pad / BM + w.wi.grid - 1) * BM;
     grad_finalize_i_kernel<T><<<cdiv(vrows * 32, 256), 256, 0, st>>>(N, B, d, w.kp, w.parts, w.N_pad, 1, 1, acci, rsi, iprep, qprep,
@@ -784,11 +841,12 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
   const int lm = sweep_lm_from_mask(desc->loss_mask);
   SideLane* lane = lm != 0 ? side_lane() : nullptr;
   if (lane != nullptr && !side_fork(lane, st)) return fail(XB_ERR_CUDA, "stream fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+  SideJoinGuard join_guard{lane, st};
   if (lm != 0) {
     rc = build_pair_mask(B, N, desc->num_pos, reinterpret_cast<const long long*>(item_idx),
                          reinterpret_cast<const long long*>(item_idx), reinterpret_cast<const long long*>(pos_idx),
                          reinterpret_cast<uint32_t*>(ws + w.mask), reinterpret_cast<uint32_t*>(ws + w.mask_t),
-                         ws + w.pm_ws, lane != nullptr ? lane->s : st);
+                         ws + w.pm_ws, lane != nullptr ? lane->s : st, lane != nullptr ? side_lane(1) : nullptr);
     if (rc != XB_OK) return rc;
   }
   // 1. operands -> bf16 (hi [, lo]) + norms
@@ -810,7 +868,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                                    reinterpret_cast<float2*>(ws + w.ipar));
   XB_LAUNCHED();
 
-  if (lane != nullptr && !side_join(lane, st)) return fail(XB_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!join_guard.join()) return fail(XB_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
   float4* rowstat = reinterpret_cast<float4*>(ws + w.rowstat);
   float* rowloss = reinterpret_cast<float*>(ws + w.rowloss);
   if (lm != 0) {
@@ -916,7 +974,10 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
                                                    reinterpret_cast<float*>(ws + w.diag), rowstat, rowloss, nullptr, nullptr);
     XB_LAUNCHED();
   }
-  {
+  if (B <= LOSS_RED_SINGLE) {
+    loss_reduce_kernel<<<XB_NUM_LOSSES, 256, 0, st>>>(B, rowloss, desc->loss_mask, losses_out);
+    XB_LAUNCHED();
+  } else {
     const int nblk = cdiv(B, LOSS_RED_ROWS);
     double* partial = reinterpret_cast<double*>(ws + w.redpart);
     loss_reduce1_kernel<<<dim3(nblk, XB_NUM_LOSSES), 256, 0, st>>>(B, rowloss, partial);

@@ -422,6 +422,22 @@ __global__ void loss_reduce1_kernel(int B, const float* __restrict__ rowloss, do
   }
   if (threadIdx.x == 0) partial[static_cast<size_t>(l) * gridDim.x + blk] = sh[0];
 }
+// one launch for batches up to LOSS_RED_SINGLE rows: block l sums loss vector l in a fixed order (fp64, deterministic)
+constexpr int LOSS_RED_SINGLE = 1 << 16;
+__global__ void __launch_bounds__(256) loss_reduce_kernel(int B, const float* __restrict__ rowloss, uint32_t loss_mask,
+                                                          float* __restrict__ losses) {
+  __shared__ double sh[256];
+  const int l = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) acc += static_cast<double>(rowloss[static_cast<size_t>(l) * B + i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) losses[l] = ((loss_mask >> l) & 1u) ? static_cast<float>(sh[0]) : 0.f;
+}
 __global__ void loss_reduce2_kernel(int nblk, const double* __restrict__ partial, uint32_t loss_mask,
                                     float* __restrict__ losses) {
   const int l = threadIdx.x;
@@ -605,6 +621,91 @@ __global__ void grad_fold_kernel(int B, int kp, int parts, int lm, const __nv_bf
     kvec[row] = live ? fabsf(g.z) : 0.f;
     if (sg < 0.f) atomicOr(csign + (row >> 5), 1u << (row & 31));
   }
+}
+
+// One launch for the backward set-up of a single-loss call: upstream gradients -> per-query coefficients (grad_coef) ->
+// folded operands of the item-major sweep (grad_fold_kernel) + sign words + |k| vector, with no memset in front of it.
+// One warp per query row of B_pad; rows >= B only clear their |k| entry.  Every warp derives the effective upstream
+// vector from d_losses itself (7 floats); block 0 also publishes it for the finalisers.
+__global__ void grad_prepare_kernel(int B, int B_pad, int kp, int parts, int lm, uint32_t loss_mask,
+                                    const float* __restrict__ d_losses, float sigma, const float4* __restrict__ qfwd,
+                                    const float4* __restrict__ rowinfo, const float4* __restrict__ rowstat,
+                                    const __nv_bfloat16* __restrict__ qprep, const float* __restrict__ qn2, float cabs,
+                                    float* __restrict__ u_eff, float* __restrict__ qg, __nv_bfloat16* __restrict__ qs,
+                                    __nv_bfloat16* __restrict__ qaug, uint32_t* __restrict__ csign,
+                                    float* __restrict__ kvec, float* __restrict__ gsign) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float u[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) u[l] = (l < 7 && ((loss_mask >> l) & 1u)) ? d_losses[l] : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x < 8) u_eff[threadIdx.x] = u[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float uu = 0.f;
+    if (lm == LM_CONTR) uu = u[1] + u[2];
+    if (lm == LM_INFONCE) uu = u[3];
+    if (lm == LM_MINE) uu = u[4];
+    if (lm == LM_HINGE) uu = u[5];
+    if (lm == LM_LOGI) uu = u[6];
+    *gsign = uu < 0.f ? -1.f : 1.f;
+  }
+  if (row >= B_pad) return;
+  auto coef_of = [&](int r, float& a2, float& off, float& k) {
+    const GradCoef g = grad_coef(u, sigma, qfwd[r], rowinfo[r], rowstat[r]);
+    a2 = g.a2;
+    off = 0.f;
+    k = 0.f;
+    if (lm == LM_CONTR) { off = g.offC; k = g.kC; }
+    if (lm == LM_INFONCE) { off = g.offI; k = g.kI; }
+    if (lm == LM_MINE) { off = g.offM; k = g.kM; }
+    if (lm == LM_HINGE) { off = g.offH; k = g.kH; }
+    if (lm == LM_LOGI) { off = g.offL; k = g.kL; }
+  };
+  auto live_of = [](float a2, float off, float k) { return k != 0.f && fabsf(k) <= 3.0e38f && fabsf(off) <= 3.0e38f && a2 != 0.f; };
+  // sign word of the 32 queries row .. row + 31 (the warp of the first of them writes it: no atomics, no memset)
+  if ((row & 31) == 0) {
+    const int r = row + lane;
+    bool neg = false;
+    if (r < B) {
+      float a2, off, k;
+      coef_of(r, a2, off, k);
+      neg = live_of(a2, off, k) && a2 < 0.f;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, neg);
+    if (lane == 0) csign[row >> 5] = word;
+  }
+  if (row >= B) {
+    if (lane == 0) kvec[row] = 0.f;
+    return;
+  }
+  float a2, off, k;
+  coef_of(row, a2, off, k);
+  if (lane == 0) reinterpret_cast<float4*>(qg)[row] = make_float4(a2, off, k, 0.f);
+  const bool expo = grad_expfast(lm);
+  const bool live = live_of(a2, off, k);
+  const float sg = !live ? 0.f : (a2 > 0.f ? 1.f : -1.f);
+  const int rowlen = parts * kp;   // multiple of 64
+  const uint4* src = reinterpret_cast<const uint4*>(qprep + static_cast<size_t>(row) * rowlen);
+  uint4* dst = reinterpret_cast<uint4*>(qs + static_cast<size_t>(row) * rowlen);
+  const uint32_t flip = sg < 0.f ? 0x80008000u : 0u;
+  for (int kk = lane; kk < rowlen / 8; kk += 32) {
+    uint4 x = src[kk];
+    if (sg == 0.f) x = make_uint4(0u, 0u, 0u, 0u);
+    else { x.x ^= flip; x.y ^= flip; x.z ^= flip; x.w ^= flip; }
+    dst[kk] = x;
+  }
+  const float o = live ? (off + (expo ? log2f(fabsf(k)) : 0.f)) / cabs : -300.f / cabs;
+  const float t = sg * (-0.5f * qn2[row]) + o;
+  const __nv_bfloat16 t0 = __float2bfloat16_rn(t);
+  const float r1 = t - __bfloat162float(t0);
+  const __nv_bfloat16 t1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 t2 = __float2bfloat16_rn(r1 - __bfloat162float(t1));
+  const __nv_bfloat16 sb = __float2bfloat16_rn(sg), zero = __float2bfloat16_rn(0.f);
+  const int c = lane & 15;
+  __nv_bfloat16 v = zero;
+  if (lane >= 16) v = c == 0 ? t0 : (c == 1 ? t1 : (c == 2 ? t2 : (c < 6 ? sb : zero)));
+  qaug[static_cast<size_t>(row) * 32 + lane] = v;
+  if (lane == 0) kvec[row] = live ? fabsf(k) : 0.f;
 }
 
 template <typename T>

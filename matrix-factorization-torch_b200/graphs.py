@@ -109,11 +109,18 @@ class GraphedLossStep:
             raise RuntimeError(msg)
         slot = self._next_slot
         consumed = self._consumed[slot]
+        # Device-resident inputs were (or are being) written on the caller's stream: the copy stream must wait for that
+        # work, and the caching allocator must not hand their memory out again while the copy is in flight.
+        on_device = [inputs[k] for k in _INPUT_KEYS if inputs[k].is_cuda]
+        if on_device:
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._copy_stream), torch.no_grad():
             if consumed is not None:
                 self._copy_stream.wait_event(consumed)  # the step that last ran on this slot has finished
             for k in _INPUT_KEYS:
                 self._inputs[slot][k].copy_(inputs[k], non_blocking=True)
+            for t in on_device:
+                t.record_stream(self._copy_stream)
             self._uploaded[slot].record(self._copy_stream)
         self._pending = slot
         self._next_slot = (slot + 1) % self.NUM_SLOTS

@@ -262,22 +262,63 @@ def arrow_to_catalog(table, *, id_col: str, text_col: str | None, embedding_col:
     return emb, ids, texts
 
 
+# the fields the reference's ``ItemProcessor`` dumps into ``processors.json`` (pydantic ``model_dump()`` of
+# xfmr_rec/data/lightning.py:79-81, :128-133, :154-165; written at xfmr_rec/lightning.py:318-322) with its defaults
+REFERENCE_ITEM_ARGS = {
+    "batch_size": 32,
+    "data_dir": "data",
+    "idx_col": "movie_rn",
+    "id_col": "movie_id",
+    "text_col": "movie_text",
+    "lance_table_name": "movies",
+    "lance_db_path": "lance_db",
+    "num_partitions": None,
+    "num_sub_vectors": None,
+    "num_probes": 8,
+    "refine_factor": 4,
+}
+
+
 class ItemProcessor:
     """Exact-search stand-in for ``xfmr_rec.data.lightning.ItemProcessor`` (search side only).
 
     ``get_index`` takes the item embeddings directly (the reference encodes them with the model,
-    data/lightning.py:182-219, which is outside this path) and keeps them on the GPU; ``search`` has the
-    reference's signature and returns the same columns (``id_col``, ``text_col``, ``score``).
+    data/lightning.py:182-219, which is outside this path) and keeps them on the GPU; ``search`` has the reference's
+    signature and returns the reference's columns: every column of the item table (``idx_col`` when known, ``id_col``,
+    ``text_col``, ``embedding``) plus ``score`` - ``recommend`` drops ``embedding`` from that frame
+    (xfmr_rec/lightning.py:93-95).
+
+    ``metric="cosine"`` (default, what the reference indexes with, data/lightning.py:222-229: ``score = 1 - cosine
+    distance``): catalog rows are L2-normalised when the index is built and queries when they are searched, so scores are
+    cosine similarities whatever the norms of the inputs.  ``metric="dot"`` scores raw inner products (identical for the
+    unit-norm embeddings the reference's model emits, xfmr_rec/models.py:59).  Item ids must be non-negative: -1 marks
+    an empty result slot (fewer than ``top_k`` candidates left after the exclusions).
+
+    The constructor also accepts (and ``save`` writes back) the other fields of the reference's ``processors.json``
+    entry, so ``ItemProcessor(**json.load(...)["items"])`` works on a reference export.
     """
 
-    def __init__(self, *, id_col: str = "movie_id", text_col: str = "movie_text", compute: str | None = None) -> None:
+    def __init__(self, *, idx_col: str = "movie_rn", id_col: str = "movie_id", text_col: str = "movie_text",
+                 compute: str | None = None, metric: str = "cosine", **reference_args: object) -> None:
+        if metric not in ("cosine", "dot"):
+            msg = f"metric must be 'cosine' or 'dot', got {metric!r}"
+            raise ValueError(msg)
+        unknown = set(reference_args) - set(REFERENCE_ITEM_ARGS) - {"items_parquet"}
+        if unknown:
+            msg = f"unknown ItemProcessor arguments: {sorted(unknown)}"
+            raise TypeError(msg)
+        self.idx_col = idx_col
         self.id_col = id_col
         self.text_col = text_col
         self.compute = compute
+        self.metric = metric
+        self.reference_args = {k: reference_args.get(k, v) for k, v in REFERENCE_ITEM_ARGS.items()
+                               if k not in ("idx_col", "id_col", "text_col")}
         self.embeddings: torch.Tensor | None = None
         self.item_ids: torch.Tensor | None = None
+        self.item_idx: torch.Tensor | None = None      # the reference's ``movie_rn`` column (host tensor), when known
         self.item_text: Sequence[str] | None = None
-        self._row_of_id: dict[int, int] | None = None   # item id -> catalog row, built on the first text lookup
+        self._row_of_id: dict[int, int] | None = None   # item id -> catalog row, built on the first lookup
 
     def get_index(
         self,
@@ -285,16 +326,25 @@ class ItemProcessor:
         item_ids: torch.Tensor | Sequence[int] | None = None,
         item_text: Sequence[str] | None = None,
         *,
+        item_idx: torch.Tensor | Sequence[int] | None = None,
         device: torch.device | str = "cuda",
     ) -> ItemProcessor:
         emb = torch.as_tensor(item_embeddings)
-        if emb.dtype not in (torch.float32, torch.bfloat16):
-            emb = emb.float()
-        self.embeddings = emb.to(device).contiguous()
+        dtype = emb.dtype if emb.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        emb = emb.to(device)
+        if self.metric == "cosine":
+            # (normalised in fp32; a bf16 index rounds afterwards: cosine of the bf16-rounded unit vectors)
+            emb = torch.nn.functional.normalize(emb.float(), dim=-1)
+        self.embeddings = emb.to(dtype).contiguous()
         if item_ids is None:
             self.item_ids = None
         else:
-            self.item_ids = torch.as_tensor(item_ids, dtype=torch.int64).to(device).contiguous()
+            ids = torch.as_tensor(item_ids, dtype=torch.int64)
+            if ids.numel() and int(ids.min()) < 0:
+                msg = "item ids must be non-negative (-1 marks an empty result slot)"
+                raise ValueError(msg)
+            self.item_ids = ids.to(device).contiguous()
+        self.item_idx = None if item_idx is None else torch.as_tensor(item_idx, dtype=torch.int64).cpu()
         self.item_text = item_text
         self._row_of_id = None
         return self
@@ -312,19 +362,27 @@ class ItemProcessor:
         """Index from the item table the reference keeps in LanceDB: ``id_col``, ``text_col`` and a
         ``fixed_size_list<float32, d>`` embedding column (data/lightning.py:189, :208-219).  ``rank`` / ``world_size``
         keep only this rank's contiguous row shard (catalog row-sharding of ``distributed.sharded_topk``)."""
+        import numpy as np  # noqa: PLC0415
+
         emb, ids, texts = arrow_to_catalog(table, id_col=self.id_col, text_col=self.text_col, embedding_col=embedding_col)
+        idx = None
+        if self.idx_col in table.column_names:
+            idx = np.ascontiguousarray(table[self.idx_col].to_numpy(), dtype=np.int64)
         if world_size > 1:
             bounds = [len(ids) * r // world_size for r in range(world_size + 1)]
             lo, hi = bounds[rank], bounds[rank + 1]
             emb, ids = emb[lo:hi], ids[lo:hi]
             texts = texts[lo:hi] if texts is not None else None
-        emb_t = torch.from_numpy(emb)
+            idx = idx[lo:hi] if idx is not None else None
+        emb_t = torch.from_numpy(np.array(emb, copy=True))
         if dtype is not None:
             emb_t = emb_t.to(dtype)
-        return self.get_index(emb_t, torch.from_numpy(ids), texts, device=device)
+        return self.get_index(emb_t, torch.from_numpy(np.array(ids, copy=True)), texts,
+                              item_idx=None if idx is None else torch.from_numpy(np.array(idx, copy=True)), device=device)
 
     def to_arrow(self):  # noqa: ANN201
-        """The index as a pyarrow table with the reference's column layout (``id_col``, ``text_col``, ``embedding``)."""
+        """The index as a pyarrow table with the reference's column layout (``idx_col`` when known, ``id_col``, ``text_col``,
+        ``embedding: fixed_size_list<float32, d>``; data/lightning.py:189, :208-219)."""
         import pyarrow as pa  # noqa: PLC0415
 
         if self.embeddings is None:
@@ -333,15 +391,20 @@ class ItemProcessor:
         emb = self.embeddings.float().cpu().numpy()
         num_items, dim = emb.shape
         ids = self.item_ids.cpu().numpy() if self.item_ids is not None else torch.arange(num_items).numpy()
-        columns = {self.id_col: pa.array(ids, type=pa.int64())}
+        columns = {}
+        if self.item_idx is not None:
+            columns[self.idx_col] = pa.array(self.item_idx.numpy(), type=pa.int64())
+        columns[self.id_col] = pa.array(ids, type=pa.int64())
         if self.item_text is not None:
             columns[self.text_col] = pa.array(list(self.item_text), type=pa.string())
         columns["embedding"] = pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1), type=pa.float32()), dim)
         return pa.table(columns)
 
     def save(self, path) -> None:  # noqa: ANN001
-        """Write the index bundle: ``items.parquet`` (reference table layout) + ``processors.json`` with the
-        processor arguments under ``"items"`` (the key the reference's export uses, xfmr_rec/lightning.py:318-322)."""
+        """Write the index bundle: ``items.parquet`` (reference table layout) + ``processors.json`` with the processor
+        arguments under ``"items"`` in the reference's schema (every field of its ``ItemProcessor.model_dump()``,
+        xfmr_rec/lightning.py:318-322) plus this class's own ``compute`` / ``metric`` / ``items_parquet`` keys, which the
+        reference's pydantic model ignores."""
         import json  # noqa: PLC0415
         import pathlib  # noqa: PLC0415
 
@@ -350,7 +413,9 @@ class ItemProcessor:
         path = pathlib.Path(path)
         path.mkdir(parents=True, exist_ok=True)
         pq.write_table(self.to_arrow(), path / ITEMS_PARQUET)
-        args = {"items": {"id_col": self.id_col, "text_col": self.text_col, "compute": self.compute}}
+        items = {**self.reference_args, "idx_col": self.idx_col, "id_col": self.id_col, "text_col": self.text_col,
+                 "compute": self.compute, "metric": self.metric, "items_parquet": ITEMS_PARQUET}
+        args = {"items": {k: items[k] for k in [*REFERENCE_ITEM_ARGS, "compute", "metric", "items_parquet"]}}
         (path / PROCESSORS_JSON).write_text(json.dumps(args, indent=2))
 
     @classmethod
@@ -366,7 +431,7 @@ class ItemProcessor:
         args = {}
         if (path / PROCESSORS_JSON).exists():
             args = json.loads((path / PROCESSORS_JSON).read_text()).get("items", {})
-        known = {k: args[k] for k in ("id_col", "text_col", "compute") if k in args}
+        known = {k: v for k, v in args.items() if k in REFERENCE_ITEM_ARGS or k in ("compute", "metric")}
         return cls(**known).get_index_from_arrow(
             pq.read_table(path / ITEMS_PARQUET), device=device, dtype=dtype, rank=rank, world_size=world_size
         )
@@ -426,6 +491,8 @@ class ItemProcessor:
         if queries.dim() == 1:
             queries = queries[None, :]
         queries = queries.to(self.embeddings.device)
+        if self.metric == "cosine":
+            queries = torch.nn.functional.normalize(queries.float(), dim=-1)
         mask, sparse = self._exclusions(exclude_item_ids, queries.size(0), top_k)
         if sparse is not None:
             fetch = top_k + sparse.size(1)
@@ -475,14 +542,22 @@ class ItemProcessor:
         scores, ids = self.search_batch(torch.as_tensor(embedding).reshape(1, -1), exclude, top_k)
         scores = scores[0].cpu()
         ids = ids[0].cpu()
-        keep = ids >= 0
-        frame = {self.id_col: ids[keep].numpy(), "score": scores[keep].numpy()}
+        keep = scores > float("-inf")               # empty slots carry score -inf (and id -1)
+        ids, scores = ids[keep], scores[keep]
+        if self.item_ids is None:
+            rows = ids.tolist()
+        else:
+            if self._row_of_id is None:   # once per index, not once per query
+                self._row_of_id = {int(v): r for r, v in enumerate(self.item_ids.cpu().tolist())}
+            rows = [self._row_of_id[int(v)] for v in ids.tolist()]
+        # the reference returns every column of the item table + score (lance ``to_pandas()``, data/lightning.py:250-259)
+        frame: dict[str, object] = {}
+        if self.item_idx is not None:
+            frame[self.idx_col] = self.item_idx[rows].numpy() if rows else self.item_idx[:0].numpy()
+        frame[self.id_col] = ids.numpy()
         if self.item_text is not None:
-            if self.item_ids is None:
-                rows = ids[keep].tolist()
-            else:
-                if self._row_of_id is None:   # once per index, not once per query
-                    self._row_of_id = {int(v): r for r, v in enumerate(self.item_ids.cpu().tolist())}
-                rows = [self._row_of_id[int(v)] for v in ids[keep].tolist()]
             frame[self.text_col] = [self.item_text[r] for r in rows]
+        emb_rows = self.embeddings[torch.as_tensor(rows, dtype=torch.int64, device=self.embeddings.device)].float().cpu().numpy()
+        frame["embedding"] = list(emb_rows)
+        frame["score"] = scores.numpy()
         return pd.DataFrame(frame)

@@ -46,14 +46,14 @@ def test_sparse_exclusions_equal_the_prefilter(nq: int, n: int, k: int, width: i
     q, it = make(nq, n, 64, nq + n)
     ids = (torch.randperm(3 * n, generator=torch.Generator().manual_seed(1))[:n] + 1).numpy()
     excl = exclusion_lists(q, it, ids, width, n_best, 0)
-    index = xfmr_b200.ItemProcessor().get_index(it, torch.from_numpy(ids))
+    index = xfmr_b200.ItemProcessor(metric="dot").get_index(it, torch.from_numpy(ids))
     index.DENSE_MASK_BYTES = 0    # force the sparse path; the dense one is covered by test_gpu_topk.py
     scores, got = index.search_batch(q, torch.from_numpy(excl), top_k=k)
     ref_s, ref_i = native.topk(q.numpy(), it.numpy(), k, item_ids=ids, exclude=excl)
     assert np.array_equal(got.cpu().numpy(), ref_i)
     assert np.array_equal(scores.cpu().numpy(), ref_s)
     # and it agrees with the dense-mask path
-    dense = xfmr_b200.ItemProcessor().get_index(it, torch.from_numpy(ids))
+    dense = xfmr_b200.ItemProcessor(metric="dot").get_index(it, torch.from_numpy(ids))
     s2, i2 = dense.search_batch(q, torch.from_numpy(excl), top_k=k)
     assert torch.equal(i2, got)
     assert torch.equal(s2, scores)
@@ -63,7 +63,7 @@ def test_exclusions_too_long_for_either_path_raise() -> None:
     import xfmr_b200  # noqa: PLC0415
 
     q, it = make(4, 500, 32, 3)
-    index = xfmr_b200.ItemProcessor().get_index(it)
+    index = xfmr_b200.ItemProcessor(metric="dot").get_index(it)
     index.DENSE_MASK_BYTES = 0
     with pytest.raises(ValueError, match="exclusion lists"):
         index.search_batch(q, torch.zeros(4, 250, dtype=torch.int64), top_k=20)
@@ -99,7 +99,7 @@ def test_batched_evaluation_matches_the_metric_oracle(nq: int, n: int, k: int) -
     ids = (torch.randperm(2 * n, generator=torch.Generator().manual_seed(2))[:n] + 1).numpy()
     excl = exclusion_lists(q, it, ids, 8, 6, 1)
     targets = targets_for(q, it, ids, 4)
-    index = xfmr_b200.ItemProcessor().get_index(it, torch.from_numpy(ids))
+    index = xfmr_b200.ItemProcessor(metric="dot").get_index(it, torch.from_numpy(ids))
     out = index.evaluate(q, [list(t) for t in targets], [list(t.values()) for t in targets], torch.from_numpy(excl), top_k=k)
     _, ref_i = native.topk(q.numpy(), it.numpy(), k, item_ids=ids, exclude=excl)
     per_query, mean = metrics_oracle.batch_metrics(ref_i.tolist(), targets, k)
@@ -137,7 +137,7 @@ def test_index_bundle_round_trip_and_sharded_load(tmp_path) -> None:  # noqa: AN
     q, it = make(20, 1500, 32, 77)
     ids = (torch.randperm(5000, generator=torch.Generator().manual_seed(3))[:1500] + 1)
     texts = [f"item {int(i)}" for i in ids]
-    index = xfmr_b200.ItemProcessor(id_col="movie_id", text_col="movie_text").get_index(it, ids, texts)
+    index = xfmr_b200.ItemProcessor(id_col="movie_id", text_col="movie_text", metric="dot").get_index(it, ids, texts)
     index.save(tmp_path / "bundle")
     loaded = xfmr_b200.ItemProcessor.load(tmp_path / "bundle")
     assert loaded.id_col == "movie_id" and loaded.item_text == texts

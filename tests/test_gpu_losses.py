@@ -282,6 +282,16 @@ def test_graphed_step_matches_eager_and_takes_host_inputs() -> None:
     # device inputs go through the same path
     res = stepper.submit({k: batches[1][k].to(dev) for k in keys})
     assert res.loss_value() == pytest.approx(results[1][0], rel=1e-6)
+    # ... also when they have just been computed on the caller's stream (the copy stream must wait for the producer and
+    # the allocator must keep the temporaries alive): a long-running producer right before the submit
+    big = torch.randn(4096, 4096, device=dev)
+    for _ in range(5):
+        big = torch.tanh(big @ big * 1e-2)
+    fresh = {k: (batches[2][k].to(dev) * 1 if batches[2][k].is_floating_point() else batches[2][k].to(dev) + 0) for k in keys}
+    fresh["user_embed"] = fresh["user_embed"] + big[:300, :64] * 0.0
+    res = stepper.submit(fresh)
+    del fresh
+    assert res.loss_value() == pytest.approx(results[2][0], rel=1e-6)
 
 
 @pytest.mark.parametrize(("k", "dtype"), [(4, torch.float32), (32, torch.float32), (8, torch.bfloat16)])

@@ -70,7 +70,7 @@ def test_exclusions_are_prefiltered() -> None:
         top = np.argsort(-full[r])[:12]
         excl[r, :12] = ids.numpy()[top]                     # exclude the 12 best of every query
         excl[r, 12:16] = rng.integers(20_000, 30_000, 4)    # ids that are not in the catalog
-    index = xfmr_b200.ItemProcessor().get_index(it, ids)
+    index = xfmr_b200.ItemProcessor(metric="dot").get_index(it, ids)
     scores, got = index.search_batch(q, torch.from_numpy(excl), top_k=20)
     ref_s, ref_i = native.topk(q.numpy(), it.numpy(), 20, item_ids=ids.numpy(), exclude=excl)
     assert np.array_equal(got.cpu().numpy(), ref_i)
@@ -115,3 +115,24 @@ def test_merge_is_deterministic_across_shardings() -> None:
         s, i = xfmr_b200.topk_merge(cat_s, cat_i, 30)
         assert torch.equal(i, base_i)
         assert torch.equal(s, base_s)
+
+
+def test_search_scores_are_cosine_similarities_by_default() -> None:
+    """The reference indexes with ``metric="cosine"`` and reports ``1 - distance`` (data/lightning.py:222-229, :257):
+    with un-normalised catalog rows and queries the default ``ItemProcessor`` must rank by cosine similarity, where raw
+    inner products rank by norm."""
+    import xfmr_b200  # noqa: PLC0415
+
+    gen = torch.Generator().manual_seed(3)
+    items = torch.randn(500, 32, generator=gen) * (0.2 + 3.0 * torch.rand(500, 1, generator=gen))
+    query = torch.randn(1, 32, generator=gen) * 7.0
+    ids = torch.arange(100, 600)
+    want = torch.nn.functional.cosine_similarity(query.double(), items.double())
+    order = want.argsort(descending=True)[:10]
+    frame = xfmr_b200.ItemProcessor().get_index(items, ids).search(query.numpy(), None, top_k=10)
+    assert frame["movie_id"].tolist() == ids[order].tolist()
+    assert frame["score"].tolist() == pytest.approx(want[order].tolist(), abs=1e-5)
+    assert list(frame.columns) == ["movie_id", "embedding", "score"]
+    dot = xfmr_b200.ItemProcessor(metric="dot").get_index(items, ids).search(query.numpy(), None, top_k=10)
+    raw = (items.double() @ query.double().t()).squeeze(1)
+    assert dot["movie_id"].tolist() == ids[raw.argsort(descending=True)[:10]].tolist()

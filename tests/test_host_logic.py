@@ -199,10 +199,15 @@ def test_exclusion_path_selection_and_padding_helpers() -> None:
 
 
 def test_search_frame_assembly_with_a_stubbed_kernel(monkeypatch) -> None:  # noqa: ANN001
-    """``ItemProcessor.search`` (data/lightning.py:237-259): result columns, empty slots dropped, text looked up by id.
-    The kernel call is stubbed: only the host-side assembly runs here."""
+    """``ItemProcessor.search`` (data/lightning.py:237-259): the reference's result columns (every table column + score),
+    empty slots dropped, rows looked up by id; then the reference's own call site, ``recommend``
+    (xfmr_rec/lightning.py:93-95: ``.search(...).drop(columns="embedding")``), and the BentoML ``ItemCandidate`` fields
+    (bentoml/service.py:52-55, :129-131: ``movie_id, movie_text, score``) replayed on the frame.  The kernel call is
+    stubbed: only the host-side assembly runs here."""
+    emb = torch.arange(32, dtype=torch.float32).reshape(4, 8) + 1.0
     index = xfmr_b200.ItemProcessor(id_col="movie_id", text_col="movie_text").get_index(
-        torch.zeros(4, 8), torch.tensor([40, 10, 30, 20]), ["forty", "ten", "thirty", "twenty"], device="cpu")
+        emb, torch.tensor([40, 10, 30, 20]), ["forty", "ten", "thirty", "twenty"], item_idx=torch.tensor([1, 2, 3, 4]), device="cpu")
+    assert torch.allclose(index.embeddings.norm(dim=-1), torch.ones(4), atol=1e-6)          # metric="cosine": unit rows
     calls = []
 
     def fake_search_batch(embedding, exclude, top_k):  # noqa: ANN001, ANN202
@@ -212,9 +217,50 @@ def test_search_frame_assembly_with_a_stubbed_kernel(monkeypatch) -> None:  # no
     monkeypatch.setattr(index, "search_batch", fake_search_batch)
     frame = index.search(torch.zeros(8).numpy(), exclude_item_ids=[10], top_k=3)
     assert calls == [((1, 8), [[10]], 3)]
-    assert list(frame.columns) == ["movie_id", "score", "movie_text"]
+    assert list(frame.columns) == ["movie_rn", "movie_id", "movie_text", "embedding", "score"]
     assert frame["movie_id"].tolist() == [30, 40] and frame["movie_text"].tolist() == ["thirty", "forty"]
+    assert frame["movie_rn"].tolist() == [3, 1]
     assert frame["score"].tolist() == pytest.approx([0.9, 0.5])
+    assert torch.allclose(torch.tensor(frame["embedding"].iloc[0]), index.embeddings[2])
+    # the reference's caller and the serving schema
+    dropped = frame.drop(columns="embedding")
+    assert list(dropped.columns) == ["movie_rn", "movie_id", "movie_text", "score"]
+    for rec in dropped.to_dict(orient="records"):
+        assert isinstance(rec["movie_id"], int) and isinstance(rec["movie_text"], str) and isinstance(rec["score"], float)
     frame2 = index.search(torch.zeros(1, 8).numpy(), None, top_k=3)            # no exclusions: None is passed through
     assert calls[-1][1] is None and frame2["movie_text"].tolist() == ["thirty", "forty"]
     assert index._row_of_id == {40: 0, 10: 1, 30: 2, 20: 3}                     # noqa: SLF001  built once, reused
+    with pytest.raises(ValueError, match="non-negative"):
+        xfmr_b200.ItemProcessor().get_index(torch.zeros(2, 8), torch.tensor([3, -7]), device="cpu")
+    raw = xfmr_b200.ItemProcessor(metric="dot").get_index(emb, device="cpu")
+    assert torch.equal(raw.embeddings, emb)                                      # metric="dot": rows as given
+
+
+def test_processors_json_follows_the_reference_schema(tmp_path) -> None:  # noqa: ANN001
+    """``save`` writes ``processors.json["items"]`` with every field of the reference's ``ItemProcessor.model_dump()``
+    (xfmr_rec/lightning.py:318-322; fields at data/lightning.py:79-81, :128-133, :154-165) and the item table with the
+    reference's columns incl. ``movie_rn``; a reference-style entry constructs the processor."""
+    import json  # noqa: PLC0415
+
+    import pyarrow.parquet as pq  # noqa: PLC0415
+
+    index = xfmr_b200.ItemProcessor().get_index(torch.eye(3, 8), torch.tensor([7, 8, 9]), ["a", "b", "c"],
+                                                item_idx=torch.tensor([1, 2, 3]), device="cpu")
+    index.save(tmp_path / "bundle")
+    items = json.loads((tmp_path / "bundle" / "processors.json").read_text())["items"]
+    reference_fields = ["batch_size", "data_dir", "idx_col", "id_col", "text_col", "lance_table_name", "lance_db_path",
+                        "num_partitions", "num_sub_vectors", "num_probes", "refine_factor"]
+    assert list(items)[: len(reference_fields)] == reference_fields
+    assert items["idx_col"] == "movie_rn" and items["lance_table_name"] == "movies" and items["num_probes"] == 8
+    table = pq.read_table(tmp_path / "bundle" / "items.parquet")
+    assert table.column_names == ["movie_rn", "movie_id", "movie_text", "embedding"]
+    import pyarrow as pa  # noqa: PLC0415
+
+    etype = table.schema.field("embedding").type
+    assert pa.types.is_fixed_size_list(etype) and etype.list_size == 8 and etype.value_type == pa.float32()
+    # a reference export's entry (no keys of ours) is accepted as constructor arguments
+    ref_entry = {k: items[k] for k in reference_fields}
+    proc = xfmr_b200.ItemProcessor(**ref_entry)
+    assert proc.idx_col == "movie_rn" and proc.reference_args["refine_factor"] == 4 and proc.metric == "cosine"
+    with pytest.raises(TypeError, match="unknown"):
+        xfmr_b200.ItemProcessor(bogus=1)
