@@ -155,7 +155,7 @@ def test_pair_mask_inside_the_loss_workspace_is_the_same_mask() -> None:
     import xfmr_b200  # noqa: PLC0415
     from oracle import losses_oracle  # noqa: PLC0415
     from xfmr_b200 import _lib, synthetic  # noqa: PLC0415
-    from xfmr_b200.losses import _loss_fwd, _make_desc  # noqa: PLC0415
+    _loss_fwd, _make_desc = xfmr_b200.losses._loss_fwd, xfmr_b200.losses._make_desc  # noqa: SLF001
 
     dev = torch.device("cuda:0")
     b, n, p = 200, 1500, 16

@@ -264,3 +264,17 @@ def test_processors_json_follows_the_reference_schema(tmp_path) -> None:  # noqa
     assert proc.idx_col == "movie_rn" and proc.reference_args["refine_factor"] == 4 and proc.metric == "cosine"
     with pytest.raises(TypeError, match="unknown"):
         xfmr_b200.ItemProcessor(bogus=1)
+
+
+def test_shim_submodules_are_the_loaded_modules() -> None:
+    """``from xfmr_b200.losses import ...`` must not execute ``losses.py`` a second time: re-defining the custom ops
+    destroys the torch library of the first definition and leaves the loss classes with a dangling operator."""
+    import importlib  # noqa: PLC0415
+    import sys  # noqa: PLC0415
+
+    import xfmr_b200  # noqa: PLC0415
+    from xfmr_b200.losses import _loss_fwd  # noqa: PLC0415
+
+    assert _loss_fwd is xfmr_b200.losses._loss_fwd  # noqa: SLF001
+    for sub in ("losses", "retrieval", "hashing", "synthetic", "graphs", "distributed", "uniformity", "_lib"):
+        assert importlib.import_module(f"xfmr_b200.{sub}") is sys.modules[f"matrix-factorization-torch_b200.{sub}"]
