@@ -484,8 +484,9 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * MAX_EPI_PARTS * w->N_pad);
   w->gdiag = take(sizeof(float) * B);
   if (w->mining) {
-    w->cand = take(sizeof(unsigned long long) * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad * MINE_CAP);
-    w->cand_cnt = take(sizeof(int) * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
+    // two candidate streams per (row, sub-chunk): the reference order and its mirror image, filled by ONE sweep
+    w->cand = take(sizeof(unsigned long long) * 2 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad * MINE_CAP);
+    w->cand_cnt = take(sizeof(int) * 2 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
     w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w->Kf);
     w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
     w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
@@ -947,12 +948,30 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       // hard mining has one continuous order (logit descending): one sweep; the second half of `sel` stays empty
       if (hard)
         XB_CUDA(cudaMemsetAsync(ws + w.sel, 0, sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w.Kf, st));
-      for (int side = 0; side < (hard ? 1 : 2); ++side) {
-        p.topk_mining = hard ? 3 : 1 + side;   // reference order, then its mirror image (see mined_forward_kernel)
+      // semi-hard order: ONE sweep keeps two candidate streams per row - the reference order and its mirror image (see
+      // mined_forward_kernel for why both are needed); XB_MINE_SWEEPS=2 runs them as two sweeps (round-1 behaviour)
+      static const bool two_sweeps = [] {
+        const char* e = std::getenv("XB_MINE_SWEEPS");
+        return e != nullptr && e[0] == '2';
+      }();
+      const int nstreams = w.fwd.nchunks * epi_parts(MODE_TOPK, 1, true);
+      const long long side_rows = static_cast<long long>(nstreams) * p.nR_pad;
+      if (hard || two_sweeps) {
+        for (int side = 0; side < (hard ? 1 : 2); ++side) {
+          p.topk_mining = hard ? 3 : 1 + side;
+          XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
+          cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
+              B, p.nR_pad, nstreams, p.cap, w.Kf, p.cand, p.cand_cnt,
+              reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
+          XB_LAUNCHED();
+        }
+      } else {
+        p.topk_mining = 4;
+        p.cand_side = side_rows;
         XB_SWEEP(launch_sweep_topk(desc->has_log_q != 0, tmQ, tmI, tmQa, tmIa, p, grid, w.fwd.smem, st));
-        cand_finalize_kernel<<<cdiv(B, 4), 128, 0, st>>>(
-            B, p.nR_pad, w.fwd.nchunks * epi_parts(MODE_TOPK, 1, true), p.cap, w.Kf, p.cand, p.cand_cnt,
-            reinterpret_cast<unsigned long long*>(ws + w.sel), 2 * w.Kf, side * w.Kf);
+        cand_finalize_kernel<<<dim3(cdiv(B, 4), 2), 128, 0, st>>>(
+            B, p.nR_pad, nstreams, p.cap, w.Kf, p.cand, p.cand_cnt, reinterpret_cast<unsigned long long*>(ws + w.sel),
+            2 * w.Kf, 0, side_rows);
         XB_LAUNCHED();
       }
       // exact re-score from the original inputs when they carry more precision than the operands

@@ -908,16 +908,20 @@ constexpr int CANDF_STAGE = 1024;   // staging entries per warp (shared memory)
 __global__ void __launch_bounds__(128) cand_finalize_kernel(int nrows, int nR_pad, int nchunks, int cap, int k,
                                      const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt,
                                      unsigned long long* __restrict__ out /*[nrows][out_stride], written at out_off*/,
-                                     int out_stride, int out_off) {
+                                     int out_stride, int out_off, long long side_rows = 0) {
   // One warp per row: the row's per-sub-chunk buffers are appended to a 1024-entry staging area in shared
   // memory; whenever the next buffer would not fit, the staging area is reduced to its k largest entries with
   // the same radix select the sweep uses.  The output is the (unordered) set of the k largest entries; callers
   // rank it themselves.  k <= 512, cap <= 1024.
+  // blockIdx.y = side (mining keeps two candidate sets per row: `side_rows` streams apart, written k entries apart).
   __shared__ unsigned long long stage[4][CANDF_STAGE];
   const int wib = threadIdx.x >> 5;
   const int row = blockIdx.x * 4 + wib;
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
+  cand += static_cast<size_t>(blockIdx.y) * side_rows * cap;
+  cand_cnt += static_cast<size_t>(blockIdx.y) * side_rows;
+  out_off += blockIdx.y * k;
   unsigned long long* st = stage[wib];
   int cnt = 0;
   for (int c = 0; c < nchunks; ++c) {
@@ -1199,24 +1203,53 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
     return use_orig ? static_cast<double>(static_cast<float>(orig_i[static_cast<size_t>(r) * d + kk]))
                     : static_cast<double>(prepped_val(ip + static_cast<size_t>(r) * parts * kp, kp, parts, kk));
   };
-  auto half_sq_dist = [&](int r) -> double {
+  // Eight lanes per candidate, four candidates per pass (the row gathers are latency-bound: a warp that walks its
+  // candidates one after the other spends ~1 us on each).  bf16 operands: 16-byte loads, 8 values per lane and pass.
+  const int grp = lane >> 3, gl = lane & 7;
+  const bool vec = !use_orig && parts == 1;
+  auto half_sq_dist = [&](int r) -> double {     // by the 8 lanes of a group; the sum ends up in all of them
     double acc = 0.0;
-    for (int kk = lane; kk < dlen; kk += 32) {
-      const double df = qval(kk) - ival(r, kk);
-      acc = fma(df, df, acc);
+    if (vec) {
+      const uint4* qv = reinterpret_cast<const uint4*>(qp + static_cast<size_t>(row) * kp);
+      const uint4* iv = reinterpret_cast<const uint4*>(ip + static_cast<size_t>(r) * kp);
+      for (int v = gl; v < (kp >> 3); v += 8) {
+        const uint4 a = qv[v], b = __ldg(iv + v);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+          // bf16 -> fp32 is a 16-bit shift
+          const double d0 = static_cast<double>(__uint_as_float(aw[w2] << 16)) - static_cast<double>(__uint_as_float(bw[w2] << 16));
+          const double d1 = static_cast<double>(__uint_as_float(aw[w2] & 0xffff0000u)) -
+                            static_cast<double>(__uint_as_float(bw[w2] & 0xffff0000u));
+          acc = fma(d0, d0, acc);
+          acc = fma(d1, d1, acc);
+        }
+      }
+    } else {
+      for (int kk = gl; kk < dlen; kk += 8) {
+        const double df = qval(kk) - ival(r, kk);
+        acc = fma(df, df, acc);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     return 0.5 * acc;
   };
   const double a2d = static_cast<double>(qf.x);
   const double dii = half_sq_dist(row);
   const double lq2i = static_cast<double>(ipar[row].y);
-  for (int s = 0; s < Kf; ++s) {
-    const unsigned long long e = cand_sel[static_cast<size_t>(row) * Kf + s];
-    if (e == 0ull) continue;  // warp-uniform
-    const int col = static_cast<int>(~static_cast<uint32_t>(e & 0xffffffffull));
-    const double dij = half_sq_dist(col);
+#pragma unroll 2
+  for (int s0 = 0; s0 < Kf; s0 += 4) {
+    const int sg = s0 + grp;
+    const unsigned long long e = sg < Kf ? cand_sel[static_cast<size_t>(row) * Kf + sg] : 0ull;
+    const int gcol = e != 0ull ? static_cast<int>(~static_cast<uint32_t>(e & 0xffffffffull)) : -1;
+    const double gdij = half_sq_dist(gcol < 0 ? 0 : gcol);
+    // candidate s belongs to lane s & 31, slot s >> 5: lanes (s0 & 31) .. + 3 fetch theirs from group 0 .. 3
+    const int rel = lane - (s0 & 31);
+    const int src = (rel & 3) * 8;
+    const double dij = __shfl_sync(0xffffffffu, gdij, src);
+    const int col = __shfl_sync(0xffffffffu, gcol, src);
+    if (rel < 0 || rel > 3 || col < 0) continue;
     const double lq2j = static_cast<double>(ipar[col].y);
     double r = a2d * (dii - dij) - (lq2j - lq2i);
     r += 0.0;  // -0 -> +0 (hard side, losses.py:149 tests `< 0`)
@@ -1227,12 +1260,11 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
     }
     key = (r != r) ? 1ull : (key < 1ull ? 1ull : key);
     const float l2 = static_cast<float>(-a2d * dij - lq2j);
-    if ((s & 31) == lane) {
 #pragma unroll
-      for (int t = 0; t < MINE_SLOTS; ++t)
-        if ((s >> 5) == t) { key_[t] = key; col_[t] = col; l2_[t] = l2; }
-    }
+    for (int t = 0; t < MINE_SLOTS; ++t)
+      if ((s0 >> 5) == t) { key_[t] = key; col_[t] = col; l2_[t] = l2; }
   }
+  __syncwarp();
   // phase 2a: drop the later copy of a column that both candidate lists delivered
 #pragma unroll
   for (int tt = 0; tt < MINE_SLOTS; ++tt) {

@@ -120,6 +120,9 @@ struct SweepParams {
   int trace_tiles;           // number of tiles traced (from tile 0 of the CTA)
   int topk_mining;           // 0: key = order(S)   1: key = bits(R) ^ 0x7fffffff, R = L2 - L2_ii (semi-hard order)
                              // 2: same with R negated (hard side first)   3: key = order(R) (hard mining, losses.py:112-132)
+                             // 4: BOTH 1 and 2 in one pass: every row keeps two candidate streams; the second one lives
+                             //    `cand_side` streams behind the first in cand / cand_cnt
+  long long cand_side;       // mode 4: rows (= streams) per side in cand / cand_cnt
   // GRAD, item-major sweep of an exponential loss (see grad_fold_kernel): the column operand is the sign-folded
   // query tile and its aug block carries the per-query offset, so x_ij = cabs * T_ij - lq2_i and |G_ij| = 2^x_ij
   float cabs;                // |sigma| * log2(e)
@@ -571,7 +574,8 @@ __device__ __forceinline__ void tmem_ld_wait_unit(uint32_t (&v)[UW]) {
   else tmem_ld_wait32(v);
 }
 
-template <int MODE, int LM, bool QROW, bool LOGQ>
+// MINE (MODE_TOPK with LM = 1 only): the mining order, compile-time copy of SweepParams::topk_mining (1, 2, 3 or 4)
+template <int MODE, int LM, bool QROW, bool LOGQ, int MINE = 0>
 __global__ void __launch_bounds__(sweep_threads(MODE, LM, QROW), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
              const __grid_constant__ CUtensorMap tmRa, const __grid_constant__ CUtensorMap tmCa, const SweepParams p) {
@@ -890,45 +894,71 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     int cnt = 0;
     uint32_t thr = row_ok ? 0u : 0xffffffffu;       // mining: entries with key <= thr can no longer enter the top `keep`
     float thr_f = row_ok ? -INFINITY : INFINITY;    // retrieval: scores below thr_f can no longer enter
-    // Mining: the keys above `thr` are a window of R = L_ij - L_ii (keys of R < 0 rank above all R >= 0, closest to
-    // 0 first).  With rt = R(thr):
-    //   semi-hard order, keep-th best semi-hard (rt < 0):   R in [rt, 0]        (mode 2, mirrored: [0, -rt])
-    //   semi-hard order, keep-th best still hard (rt >= 0): R <= rt             (mode 2: R >= -rt)
-    //   hard order (mode 3):                                R >= rt
-    // The vote evaluates u = wa * S + wb per element (wa = +-a2) and tests |u| <= whalf for a two-sided window,
-    // u <= whalf for a one-sided one (`wone`); whalf carries a rounding slack, the exact key decides on the append path.
-    float wa = rp_reg[0], wb = 0.f, whalf = -1.f;
-    bool wopen = false, wone = false, wneg = false;   // wneg: u is evaluated on -R (wa = -a2)
+    // Mining: the keys above `thr` are a window [lo, hi] of R = L_ij - L_ii (keys of R < 0 rank above all R >= 0,
+    // closest to 0 first).  With rt = R(thr):
+    //   semi-hard order, keep-th best semi-hard (rt < 0):   R in [rt, 0]        (MINE 2, mirrored: [0, -rt])
+    //   semi-hard order, keep-th best still hard (rt >= 0): R <= rt             (MINE 2: R >= -rt)
+    //   hard order (MINE 3):                                R >= rt
+    //   MINE 4 keeps the mirrored stream beside the first one (own count and threshold): ONE window, the hull of both.
+    // Every shape - two-sided, one-sided, open, empty - is ONE quadratic in u = a2 * S + wb (- lq_j):
+    //   d = (wq * u + wl) * u + wc >= 0   <=>   the element may be a candidate
+    // (two-sided: wb = c0 - centre, d = h^2 - u^2; one-sided: d = slack -+ u; open: d = 1; empty: d = -1), so a unit costs
+    // three packed FMAs per element pair and one funnel shift per element that collects the sign bits of d: no min
+    // tree, no separate vote, no per-shape branches.  The window carries a rounding slack; the exact key decides below.
+    float wb = 0.f, wq = 0.f, wl = 0.f, wc = -1.f;
+    int cntB = 0;
+    uint32_t thrB = row_ok ? 0u : 0xffffffffu;
+    // interval [lo, hi] of R whose keys lie above threshold `t` of a stream (mirrored: the stream orders -R)
+    auto key_window = [&](uint32_t t, bool mirrored, float& lo, float& hi) {
+      if (t == 0xffffffffu) { lo = INFINITY; hi = -INFINITY; return; }     // dead row: empty
+      const float rt = __uint_as_float(t ^ 0x7fffffffu);
+      float l = -INFINITY, h = INFINITY;                                    // no threshold yet
+      if (t != 0u && fabsf(rt) < INFINITY) {
+        if (t & 0x80000000u) { l = rt; h = 0.f; }                           // keep-th best on the near side: [rt, 0]
+        else h = rt;                                                        // still on the far side: R' <= rt
+      }
+      lo = mirrored ? -h : l;
+      hi = mirrored ? -l : h;
+    };
     auto set_window = [&]() {
-      const float a2 = rp_reg[0], c0 = rp_reg[2];
-      wopen = false;
-      wone = true;
-      wneg = false;
-      wa = a2;
+      const float c0 = rp_reg[2];
+      float lo, hi;
+      if (MINE == 3) {                              // hard order: R >= rt
+        const float rt = order_key_inv(thr);
+        lo = -INFINITY;
+        hi = INFINITY;
+        if (thr == 0xffffffffu) { lo = INFINITY; hi = -INFINITY; }
+        else if (thr != 0u && fabsf(rt) < INFINITY) lo = rt;
+      } else {
+        key_window(thr, MINE == 2, lo, hi);
+        if (MINE == 4) {
+          float lo2, hi2;
+          key_window(thrB, true, lo2, hi2);
+          lo = fminf(lo, lo2);
+          hi = fmaxf(hi, hi2);
+        }
+      }
       wb = 0.f;
-      whalf = -1.f;
-      if (thr == 0xffffffffu) { wb = INFINITY; return; }   // dead row: u = +inf (or NaN) never passes `u <= whalf`
-      const int mode = p.topk_mining;
-      const float rt = mode == 3 ? order_key_inv(thr) : __uint_as_float(thr ^ 0x7fffffffu);
-      if (thr == 0u || !(fabsf(rt) < INFINITY)) { wopen = true; return; }   // no threshold yet
-      const float slack = 1e-6f * (fabsf(c0) + fabsf(rt)) + 1e-30f;
-      if (mode == 3) {                              // R >= rt  <=>  -(R - rt) <= 0
-        wneg = true;
-        wa = -a2;
-        wb = rt - c0;
-        whalf = slack;
-      } else if (thr & 0x80000000u) {               // two-sided: [rt, 0] or its mirror image [0, -rt]
-        wone = false;
-        wb = c0 - (mode == 2 ? -0.5f * rt : 0.5f * rt);
-        whalf = -0.5f * rt + slack;
-      } else if (mode == 2) {                       // -R <= rt
-        wneg = true;
-        wa = -a2;
-        wb = -c0 - rt;
-        whalf = slack;
-      } else {                                      // R <= rt
-        wb = c0 - rt;
-        whalf = slack;
+      wq = 0.f;
+      wl = 0.f;
+      wc = -1.f;
+      if (lo > hi) return;                          // empty
+      const bool lo_inf = !(lo > -INFINITY), hi_inf = !(hi < INFINITY);
+      if (lo_inf && hi_inf) { wc = 1.f; return; }   // open
+      const float slack = 1e-6f * (fabsf(c0) + fmaxf(lo_inf ? 0.f : fabsf(lo), hi_inf ? 0.f : fabsf(hi))) + 1e-30f;
+      if (lo_inf) {                                 // u = R - hi <= slack
+        wb = c0 - hi;
+        wl = -1.f;
+        wc = slack;
+      } else if (hi_inf) {                          // u = R - lo >= -slack
+        wb = c0 - lo;
+        wl = 1.f;
+        wc = slack;
+      } else {                                      // |R - centre| <= h
+        wb = c0 - 0.5f * (lo + hi);
+        const float h = fmaxf(0.5f * (hi - lo) + slack, 1e-18f);
+        wq = -1.f;
+        wc = h * h;
       }
     };
     if (MODE == MODE_TOPK && LM != 0) set_window();
@@ -1170,24 +1200,36 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
           // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
           // column wins ties).
+          // (mining mode 4: the same for the mirrored stream of each row - one loop over the sides, so that the bit search
+          //  and the window update are inlined once per unit copy)
           auto compact_full_rows = [&]() {
-            uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
-            while (need) {
-              const int src = __ffs(need) - 1;
-              need &= need - 1;
-              unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
-              const int n = __shfl_sync(0xffffffffu, cnt, src);
-              __syncwarp();
-              int kept = p.keep;
-              // (a quarter more than `keep` may survive: the bit search then stops about half-way)
-              const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
-              __syncwarp();
-              if (lane == src) {
-                cnt = kept;
-                const uint32_t kk = static_cast<uint32_t>(kth >> 32);
-                thr = kk > 0 ? kk - 1 : 0;
-                thr_f = order_key_inv(kk);
-                if (MINING) set_window();
+            constexpr int nsides = (MINING && MINE == 4) ? 2 : 1;
+            for (int side = 0; side < nsides; ++side) {
+              const int mycnt = side ? cntB : cnt;
+              uint32_t need = __ballot_sync(0xffffffffu, mycnt > p.cap - 16);
+              while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                unsigned long long* buf = p.cand + (side * p.cand_side + out_row - lane + src) * p.cap;
+                const int n = __shfl_sync(0xffffffffu, mycnt, src);
+                __syncwarp();
+                int kept = p.keep;
+                // (a quarter more than `keep` may survive: the bit search then stops about half-way)
+                const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
+                __syncwarp();
+                if (lane == src) {
+                  const uint32_t kk = static_cast<uint32_t>(kth >> 32);
+                  const uint32_t nthr = kk > 0 ? kk - 1 : 0;
+                  if (side) {
+                    cntB = kept;
+                    thrB = nthr;
+                  } else {
+                    cnt = kept;
+                    thr = nthr;
+                    thr_f = order_key_inv(kk);
+                  }
+                  if (MINING) set_window();
+                }
               }
             }
           };
@@ -1225,35 +1267,31 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             // R asc; mode 2 mirrors the order, mode 3 = hard mining orders by R desc).  Keys above the threshold form a
             // WINDOW of R (see set_window), so the vote needs one FMA per element, u = R - window centre, and a min
             // tree over |u| (mode 3: a max tree over u); the window is conservative, the exact key decides below.
-            auto uval = [&](int c) {
-              float x = fmaf(wa, __uint_as_float(s[c]), wb);
-              if (LOGQ) {
-                // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
-                //  per-tile barrier, so a compacting warp never stalls the others)
-                const int jc = min(j0 + ucol + c, p.nC - 1);
-                const float lq = __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
-                x -= wneg ? -lq : lq;
-              }
-              return x;
-            };
-            const bool hard_order = p.topk_mining == 3;
-            // two min trees: over |u| (two-sided windows) and over u (one-sided); NaN operands drop out of fminf
-            float a0 = INFINITY, o0 = INFINITY;
+            // candidate bits of the unit: sign bits of the window quadratic (see set_window)
+            uint32_t pm = 0u;
+            {
+              const float a2 = rp_reg[0];
+              const float2 av = make_float2(a2, a2), bv = make_float2(wb, wb), qv = make_float2(wq, wq),
+                           lv = make_float2(wl, wl), cv = make_float2(wc, wc);
 #pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-              const float x = uval(c), y = uval(c + 1);
-              a0 = fminf(a0, fminf(fabsf(x), fabsf(y)));
-              o0 = fminf(o0, fminf(x, y));
+              for (int c = 0; c < 16; c += 2) {
+                float2 u = ffma2(av, make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), bv);
+                if (LOGQ) {
+                  // (LogQ term straight from global memory, one address per warp: the top-k epilogue has no
+                  //  per-tile barrier, so a compacting warp never stalls the others)
+                  const int jc = min(j0 + ucol + c, p.nC - 1), jc1 = min(j0 + ucol + c + 1, p.nC - 1);
+                  u.x -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
+                  u.y -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc1).y;
+                }
+                const float2 dd = ffma2(ffma2(qv, u, lv), u, cv);
+                pm = __funnelshift_l(__float_as_uint(dd.x), pm, 1);
+                pm = __funnelshift_l(__float_as_uint(dd.y), pm, 1);
+              }
+              pm = (__brev(~pm) >> 16) & ~mu;                        // element c at bit c; set <=> d >= 0 (or NaN)
             }
-            const bool hit = wopen || (wone ? o0 : a0) <= whalf;
-            if (__ballot_sync(0xffffffffu, hit)) {
-              uint32_t pm = 0u;
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float x = uval(c);
-                pm |= (wopen || (wone ? x : fabsf(x)) <= whalf) ? (1u << c) : 0u;
-              }
-              pm &= ~mu;
+            constexpr bool hard_order = MINE == 3;
+            const bool any = __ballot_sync(0xffffffffu, pm != 0u) != 0u;
+            if (any) {
               if (pm) {
                 // only lanes with a candidate park their 16 raw scores (dynamic indexing) and evaluate exact keys
                 uint32_t* mine = sStage + (warp * 32 + lane) * TOPK_STAGE_STRIDE;
@@ -1269,15 +1307,27 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                     l2 -= __ldg(reinterpret_cast<const float2*>(p.cpar) + jc).y;
                   }
                   float r = l2 + rp_reg[2];                          // rp_reg[2] = -L2_ii: R = L_ij - L_ii
-                  if (p.topk_mining == 2) {
+                  const uint32_t ent_lo = static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+                  if (MINE == 4) {
+                    // both orders from one score: the reference order on R, the mirror image on -R (an exact 0 belongs to
+                    // BOTH first groups: -0 -> +0 on the first side, 0 -> -0 on the mirrored one)
+                    const float ra = r + 0.0f;
+                    const float rm = (r == 0.f) ? -0.0f : -r;
+                    uint32_t ka = __float_as_uint(ra) ^ 0x7fffffffu, km = __float_as_uint(rm) ^ 0x7fffffffu;
+                    ka = (r != r) ? 1u : max(ka, 1u);
+                    km = (r != r) ? 1u : max(km, 1u);
+                    if (ka > thr) cb[cnt++] = (static_cast<unsigned long long>(ka) << 32) | ent_lo;
+                    if (km > thrB) cb[p.cand_side * p.cap + cntB++] = (static_cast<unsigned long long>(km) << 32) | ent_lo;
+                    continue;
+                  }
+                  if (MINE == 2) {
                     r = (r == 0.f) ? -0.0f : -r;                     // mirrored order; an exact 0 belongs to BOTH first groups
                   } else {
                     r += 0.0f;                                       // -0 -> +0 (losses.py:149 tests `< 0`)
                   }
                   uint32_t kk = hard_order ? order_key(r) : (__float_as_uint(r) ^ 0x7fffffffu);
                   kk = (r != r) ? 1u : max(kk, 1u);
-                  if (kk > thr)
-                    cb[cnt++] = (static_cast<unsigned long long>(kk) << 32) | static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+                  if (kk > thr) cb[cnt++] = (static_cast<unsigned long long>(kk) << 32) | ent_lo;
                 }
               }
               __syncwarp();
@@ -1419,6 +1469,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     }
     if (MODE == MODE_TOPK) {
       p.cand_cnt[out_row] = cnt;
+      if (LM != 0 && MINE == 4) p.cand_cnt[p.cand_side + out_row] = cntB;
     }
     if (HAS_G && more_blocks) {
       // the accumulator is in registers / memory: the second MMA of the next row block may overwrite it

@@ -33,12 +33,9 @@ class _AllGatherRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, group) -> torch.Tensor:  # noqa: ANN001
-        world = dist.get_world_size(group)
         ctx.group = group
         ctx.rows = x.size(0)
-        out = [torch.empty_like(x) for _ in range(world)]
-        dist.all_gather(out, x.contiguous(), group=group)
-        return torch.stack(out)  # [G, rows, d]
+        return _gather_plain(x, group)  # [G, rows, d]
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):  # noqa: ANN001, ANN205
@@ -55,10 +52,15 @@ class _AllGatherRows(torch.autograd.Function):
 
 
 def _gather_plain(x: torch.Tensor, group) -> torch.Tensor:  # noqa: ANN001
+    """[rows, ...] per rank -> [G, rows, ...]: ONE collective straight into the stacked buffer (no per-rank list + stack)."""
     world = dist.get_world_size(group)
-    out = [torch.empty_like(x) for _ in range(world)]
-    dist.all_gather(out, x.contiguous(), group=group)
-    return torch.stack(out)
+    x = x.contiguous()
+    out = x.new_empty((world, *x.shape))
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, x, group=group)
+    else:  # gloo: all_gather_into_tensor is not available for every dtype / version
+        dist.all_gather(list(out.unbind(0)), x, group=group)
+    return out
 
 
 def _own_first(stacked: torch.Tensor, rank: int) -> torch.Tensor:

@@ -77,7 +77,8 @@ def test_exclusions_are_prefiltered() -> None:
     assert np.array_equal(scores.cpu().numpy(), ref_s)
     # single-query DataFrame API of the reference
     frame = index.search(q[0].numpy(), exclude_item_ids=[int(x) for x in excl[0] if x != native.PAD_ID], top_k=20)
-    assert list(frame.columns)[:2] == ["movie_id", "score"]
+    assert list(frame.columns) == ["movie_id", "embedding", "score"]   # lance's to_pandas(): table columns, then the score
+    assert np.array_equal(np.stack(frame["embedding"].to_numpy()), it.numpy()[[ids.tolist().index(i) for i in frame["movie_id"]]])
     assert frame["movie_id"].tolist() == ref_i[0].tolist()
     assert frame["score"].is_monotonic_decreasing
     # no exclusions at all (the reference substitutes [0])
