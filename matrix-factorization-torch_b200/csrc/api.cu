@@ -404,7 +404,18 @@ static int mine_cap_for(int keep) {
   return cap < MINE_CAP ? cap : MINE_CAP;
 }
 constexpr int MINE_KMAX = 64;    // largest supported num_negatives
-constexpr int MINE_OVERFETCH = 16;  // extra candidates per side re-scored exactly before the final selection
+// Extra candidates per side that are re-scored exactly (fp64) before the final selection.  The sweep ranks by tensor-core
+// scores; a column can only change places with the K-th best if its exact key lies within the score error of it.  bf16
+// operands: exact products, fp32 accumulation - ~1e-6 relative, a handful of columns at most even for dense catalogs;
+// split-bf16 (fp32 inputs): 2^-16 relative, so twice the margin.  XB_MINE_OVERFETCH overrides (experiments).
+static int mine_overfetch(int parts) {
+  static const int forced = [] {
+    const char* e = std::getenv("XB_MINE_OVERFETCH");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced >= 1 && forced <= 64) return forced;
+  return parts == 2 ? 16 : 8;
+}
 
 struct LossWs {
   int kp, parts, B_pad, N_pad, words, words_t, K, Kf;
@@ -426,7 +437,7 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->words_t = mask_words_for(B);
   w->K = d->num_negatives;
   w->mining = d->num_negatives > 0 && d->num_negatives < N;
-  w->Kf = w->K + MINE_OVERFETCH;
+  w->Kf = w->K + mine_overfetch(w->parts);
   const int lm = sweep_lm_from_mask(d->loss_mask);
   const int gq_floats = grad_qpar_floats(lm == 0 ? LM_CONTR : lm);
   w->fwd = plan_sweep(B, N, w->kp, w->parts, false, true, 2, w->mining ? 4 * epi_parts(MODE_TOPK, 1, true) : 0);
