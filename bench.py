@@ -2,8 +2,8 @@
 
 Headline (BASELINE.json: "top-100 retrieval queries/s at 1/2/4/8 B200; fused loss fwd+bwd samples/s"):
 **exact top-100 retrieval queries/s on config 5** - 65,536 queries x 100,000,000 items, d=128 bf16 - with the
-catalog row-sharded over the N ranks and a query-sharded NCCL merge of the per-shard lists (`xfmr_b200.distributed.
-sharded_topk`): STRONG scaling, the one multi-GPU path of this repository that exchanges data.  A "step" is one search
+catalog row-sharded over the ranks and a query-sharded NCCL merge of the per-shard lists (`xfmr_b200.distributed.
+RetrievalGrid` / `sharded_topk`; `--retrieval-shards R` selects R shards x N / R query groups instead): STRONG scaling, the one multi-GPU path of this repository that exchanges data.  A "step" is one search
 of all 65,536 queries.  `value` times the steps with the queries resident on the device; `e2e` takes the queries from
 pinned host memory and brings scores + ids back to the host inside the timed region, through the same public call.
 
@@ -347,18 +347,27 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
 
     synthetic = load_synthetic()
     num_items_total, num_queries, k, d = args.retrieval_items, args.retrieval_queries, C5["k"], C5["dim"]
-    shard = num_items_total // world
-    items = synthetic.make_catalog(shard, d, seed=100 + rank, device=device, dtype=torch.bfloat16)
+    # layout: R catalog shards x (world / R) query groups; rank r owns shard r % R and query group r // R.  Default R = world:
+    # plain row sharding, the fastest layout measured at config 5 (profiles/r02_layouts_8gpu.txt)
+    n_shards = args.retrieval_shards or world
+    grid = xfmr_b200.distributed.RetrievalGrid(n_shards) if world > 1 else None
+    shard_idx = grid.shard if grid else 0
+    shard = num_items_total // n_shards
+    items = synthetic.make_catalog(shard, d, seed=100 + shard_idx, device=device, dtype=torch.bfloat16)
     queries = synthetic.make_catalog(num_queries, d, seed=7, device=device, dtype=torch.bfloat16)
     queries_host = queries.cpu().pin_memory()
+    queries_per_rank_group = num_queries // (grid.query_groups if grid else 1)
 
     def search(qs: torch.Tensor, kk: int) -> tuple[torch.Tensor, torch.Tensor]:
-        return xfmr_b200.topk_search(qs, items, kk, id_base=rank * shard)
+        return xfmr_b200.topk_search(qs, items, kk, id_base=shard_idx * shard)
 
     def step(qs: torch.Tensor = queries) -> tuple[torch.Tensor, torch.Tensor]:
-        if world > 1:
-            return xfmr_b200.distributed.sharded_topk(search, xfmr_b200.topk_merge, qs, k)
-        return search(qs, k)
+        return step_n(k, qs)
+
+    def step_n(kk: int, qs: torch.Tensor = queries) -> tuple[torch.Tensor, torch.Tensor]:
+        if grid:
+            return grid.search(search, xfmr_b200.topk_merge, qs, kk)
+        return search(qs, kk)
 
     def barrier() -> None:
         torch.cuda.synchronize()
@@ -417,15 +426,15 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
         sc = qf @ items[lo:lo + chunk].float().t()
         top_s, top_i = sc.topk(min(k, sc.size(1)), dim=1)
         cat_s = torch.cat([best_s, top_s], dim=1)
-        cat_i = torch.cat([best_i, top_i + (rank * shard + lo)], dim=1)
+        cat_i = torch.cat([best_i, top_i + (shard_idx * shard + lo)], dim=1)
         best_s, sel = cat_s.topk(k, dim=1)
         best_i = cat_i.gather(1, sel)
         del sc
-    if world > 1:
-        all_s = [torch.empty_like(best_s) for _ in range(world)]
-        all_i = [torch.empty_like(best_i) for _ in range(world)]
-        dist.all_gather(all_s, best_s)
-        dist.all_gather(all_i, best_i)
+    if grid:   # one copy of every shard: the ranks of this rank's catalog group
+        all_s = [torch.empty_like(best_s) for _ in range(grid.shards)]
+        all_i = [torch.empty_like(best_i) for _ in range(grid.shards)]
+        dist.all_gather(all_s, best_s, group=grid.catalog_group)
+        dist.all_gather(all_i, best_i, group=grid.catalog_group)
         cat_s, cat_i = torch.cat(all_s, dim=1), torch.cat(all_i, dim=1)
         best_s, sel = cat_s.topk(k, dim=1)
         best_i = cat_i.gather(1, sel)
@@ -439,19 +448,23 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
     n_excl = 64
 
     def search_excl(qs: torch.Tensor, kk: int) -> tuple[torch.Tensor, torch.Tensor]:
-        s_, i_ = xfmr_b200.topk_search(qs, items, kk + n_excl, id_base=rank * shard)
-        return xfmr_b200.topk_filter(s_, i_, excl, kk)
+        s_, i_ = xfmr_b200.topk_search(qs, items, kk + n_excl, id_base=shard_idx * shard)
+        return xfmr_b200.topk_filter(s_, i_, excl_mine, kk)
 
     def step_excl() -> tuple[torch.Tensor, torch.Tensor]:
-        if world > 1:
-            return xfmr_b200.distributed.sharded_topk(search_excl, xfmr_b200.topk_merge, queries, k)
+        if grid:
+            return grid.search(search_excl, xfmr_b200.topk_merge, queries, k)
         return search_excl(queries, k)
 
-    if world > 1:
-        _, excl = xfmr_b200.distributed.sharded_topk(search, xfmr_b200.topk_merge, queries, n_excl)
-    else:
-        _, excl = search(queries, n_excl)
+    _, excl = step_n(n_excl)
     excl = excl.contiguous()
+    excl_mine = excl
+    if grid and grid.query_groups > 1:   # the exclusion lists of the queries this rank's group searches (padded like them)
+        excl_mine = excl[grid.query_slice(num_queries)]
+        short = grid.rows_per_group(num_queries) - excl_mine.size(0)
+        if short:
+            excl_mine = torch.cat([excl_mine, excl_mine.new_full((short, n_excl), -1)])
+        excl_mine = excl_mine.contiguous()
     step_excl()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -468,7 +481,7 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
     del items
     torch.cuda.empty_cache()
     pk = peaks()
-    flops_per_rank = 2.0 * num_queries * shard * d
+    flops_per_rank = 2.0 * queries_per_rank_group * shard * d
     sweep_ms = sweep_ms_total / max(sweep_count, 1)
     achieved = flops_per_rank / (sweep_ms * 1e-3) / 1e12
     return {
@@ -479,8 +492,11 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
                             "read back into pinned memory; host waits for the step before starting the next"},
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": ncu_traffic("topk_sweep_dram_bytes_per_launch"),
-            "kernel": "xb::sweep_kernel<MODE_TOPK> (one launch per search and rank)",
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": (None if ncu_traffic("topk_sweep_dram_bytes_per_item") is None
+                        else ncu_traffic("topk_sweep_dram_bytes_per_item") * shard),
+            "traffic_note": "ncu capture on a 12.5M-item shard scaled by the items per rank; the catalog does not fit the 126 MB "
+                            "L2, each 64 MB chunk is re-read once per wave of query-tile pairs (DESIGN.md 3.5)",
+            "kernel": "xb::rt_kernel (one launch per search and rank)",
             "algorithmic_flops_per_launch": flops_per_rank, "launch_ms": sweep_ms, "launches_timed": sweep_count,
             "peak_source": pk["source"] + " sustained bf16 (the launch lasts seconds under the power cap)",
             "frac_of_burst_peak": achieved / pk["bf16_tflops"],
@@ -488,6 +504,8 @@ def bench_retrieval(device: torch.device, world: int, rank: int, args: argparse.
         },
         "recall_at_k_sampled": {"value": recall, "queries": 64, "against": "fp32 brute force over all shards on the same bf16 values"},
         "with_64_exclusions_per_query": {"value": num_queries / (ms_excl * 1e-3), "unit": UNIT, "ms": ms_excl},
+        "layout": {"catalog_shards": n_shards, "query_groups": grid.query_groups if grid else 1, "items_per_rank": shard,
+                   "queries_per_rank": queries_per_rank_group},
     }
 
 
@@ -771,6 +789,9 @@ def main() -> None:
     ap.add_argument("--retrieval-items", type=int, default=C5["num_items"],
                     help="catalog rows summed over all ranks (config 5: 100,000,000 = 25.6 GB bf16)")
     ap.add_argument("--retrieval-queries", type=int, default=C5["num_queries"])
+    ap.add_argument("--retrieval-shards", type=int, default=0,
+                    help="catalog shards R (a divisor of N); the N / R query groups each search a slice of the queries. "
+                         "0 = N: plain row sharding")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -805,8 +826,10 @@ def main() -> None:
             "data": "synthetic", "config": workload_config(args.retrieval_items, args.retrieval_queries),
             "clocks": clocks.summary(), "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"],
             "recall_at_k_sampled": r["recall_at_k_sampled"], "with_64_exclusions_per_query": r["with_64_exclusions_per_query"],
-            "parallelism": f"catalog row-sharded {world} ways; queries replicated; per-shard top-k lists exchanged with all_to_all, merged "
-                           "per query slice, all-gathered",
+            "parallelism": (f"catalog row-sharded {r['layout']['catalog_shards']} ways x {r['layout']['query_groups']} query groups "
+                            f"({r['layout']['items_per_rank']} items and {r['layout']['queries_per_rank']} queries per rank); per-shard "
+                            "top-k lists exchanged with all_to_all inside a query group, merged per query slice, all-gathered over all ranks"),
+            "layout": r["layout"],
         }
         if rank == 0 and world == 1:
             line["loss"] = bench_loss(device, world, rank, args)

@@ -15,7 +15,7 @@ names, vals = [names[i] for i in keep], [vals[i] for i in keep]
 s, e = 0, len(names)
 tot = sum(vals[s:e])
 print(f"one step (forward + backward): {e - s} launches, {tot / 1e3:.1f} us under ncu (cold caches, serialised)")
-sweeps = sum(v for n, v in zip(names[s:e], vals[s:e]) if "sweep_kernel" in n)
+sweeps = sum(v for n, v in zip(names[s:e], vals[s:e]) if ("sweep_kernel" in n or "wg_kernel" in n or "rt_kernel" in n))
 print(f"sweep kernels: {sweeps / 1e3:.1f} us = {100 * sweeps / tot:.1f} % of the step")
 for n, v in zip(names[s:e], vals[s:e]):
     print(f"  {v / 1e3:9.2f} us  {n[:120]}")

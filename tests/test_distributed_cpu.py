@@ -170,3 +170,46 @@ def test_shard_local_exclusions_equal_the_global_prefilter() -> None:
     out = manager.dict()
     mp.spawn(_sharded_exclusions_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _retrieval_grid_worker(rank: int, world: int, port: int, out: dict) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import xfmr_b200  # noqa: PLC0415
+    from oracle import native  # noqa: PLC0415
+
+    rng = np.random.default_rng(5)
+    queries = rng.standard_normal((10, 16)).astype(np.float32)   # 2 query groups x 5 rows -> padded to 6 per group
+    catalog = rng.standard_normal((97, 16)).astype(np.float32)
+    catalog[60] = catalog[3]                        # a tie across shards: the lower id must win
+    grid = xfmr_b200.distributed.RetrievalGrid(2)   # 4 ranks = 2 catalog shards x 2 query groups
+    bounds = np.linspace(0, 97, grid.shards + 1).astype(int)
+    lo, hi = bounds[grid.shard], bounds[grid.shard + 1]
+
+    def search(q: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        s, i = native.topk(q.numpy(), catalog[lo:hi], k, id_base=int(lo))
+        return torch.from_numpy(s), torch.from_numpy(i)
+
+    def merge(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        rows_s, rows_i = [], []
+        for r in range(scores.size(0)):
+            pairs = sorted(((-float(s), int(i)) for s, i in zip(scores[r], ids[r]) if int(i) >= 0))[:k]
+            rows_s.append([-p[0] for p in pairs])
+            rows_i.append([p[1] for p in pairs])
+        return torch.tensor(rows_s, dtype=torch.float32), torch.tensor(rows_i, dtype=torch.int64)
+
+    s, i = grid.search(search, merge, torch.from_numpy(queries), 7)
+    ref_s, ref_i = native.topk(queries, catalog, 7)
+    ok = (grid.shards, grid.query_groups, grid.shard, grid.query_group) == (2, 2, rank % 2, rank // 2)
+    out[rank] = bool(ok and np.array_equal(i.numpy(), ref_i) and np.array_equal(s.numpy(), ref_s))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_retrieval_grid_two_shards_by_two_query_groups() -> None:
+    """2-D layout (catalog shards x query groups) on 4 gloo ranks equals the unsharded search, ties and padding included."""
+    world = 4
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_retrieval_grid_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
