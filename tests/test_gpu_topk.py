@@ -137,3 +137,71 @@ def test_search_scores_are_cosine_similarities_by_default() -> None:
     dot = xfmr_b200.ItemProcessor(metric="dot").get_index(items, ids).search(query.numpy(), None, top_k=10)
     raw = (items.double() @ query.double().t()).squeeze(1)
     assert dot["movie_id"].tolist() == ids[raw.argsort(descending=True)[:10]].tolist()
+
+
+def _brute_force_must_have(q: torch.Tensor, it: torch.Tensor, k: int, allowed: torch.Tensor | None = None):  # noqa: ANN202
+    """fp32 scores of the bf16 values; per query the rows that MUST be returned (score above the k-th by a margin that
+    covers fp32 accumulation order) and the k-th score itself."""
+    sc = q.float() @ it.float().t()
+    if allowed is not None:
+        sc = sc.masked_fill(~allowed, float("-inf"))
+    kk = min(k, it.size(0))
+    top_s, _ = sc.topk(kk, dim=1)
+    kth = top_s[:, -1:]
+    return sc, (sc > kth + 2e-6) & torch.isfinite(sc), kth
+
+
+@pytest.mark.parametrize(("nq", "n", "d", "k"), [
+    (1, 1, 64, 1),            # a single pair
+    (33, 300, 64, 7),         # ragged query tile, three item tiles
+    (257, 5000, 96, 100),     # d not a multiple of 64 (zero-padded K block), one row into a second query-tile pair
+    (700, 128, 128, 128),     # exactly one item tile, k = every item
+    (512, 70_000, 128, 256),  # k at the ABI maximum
+])
+def test_bf16_retrieval_kernel_edge_shapes(nq: int, n: int, d: int, k: int) -> None:
+    """The bf16 retrieval kernel (``csrc/sweep_rt.cuh``) on ragged / minimal / maximal shapes: every row that beats the k-th
+    score clearly is returned, nothing below the k-th score is, scores are the fp32 dot products of the bf16 values,
+    lists are sorted, slots beyond the catalog are (-inf, -1)."""
+    import xfmr_b200  # noqa: PLC0415
+
+    q, it = make(nq, n, d, 3 * nq + n)
+    q, it = q.cuda().bfloat16(), it.cuda().bfloat16()
+    scores, got = xfmr_b200.topk_search(q, it, k)
+    sc, must, kth = _brute_force_must_have(q, it, k)
+    kk = min(k, n)
+    assert bool((got[:, :kk] >= 0).all()) and bool((got[:, kk:] == -1).all())
+    assert bool(torch.isinf(scores[:, kk:]).all())
+    returned = torch.zeros_like(must)
+    returned.scatter_(1, got[:, :kk], True)
+    assert bool((returned | ~must).all()), "a row above the k-th score is missing"
+    picked = sc.gather(1, got[:, :kk])
+    assert bool((picked >= kth - 2e-6).all()), "a row below the k-th score was returned"
+    assert torch.allclose(scores[:, :kk], picked, rtol=0, atol=2e-6)
+    assert bool((scores[:, 1:kk] <= scores[:, : kk - 1]).all())
+
+
+def test_bf16_retrieval_kernel_with_exclusion_mask() -> None:
+    """bf16 search with per-query exclusion lists through the dense bit mask (``rt_kernel<HAS_MASK>``): no excluded id comes
+    back and the allowed rows above the k-th allowed score all do."""
+    import xfmr_b200  # noqa: PLC0415
+
+    nq, n, d, k = 130, 3000, 64, 20
+    q, it = make(nq, n, d, 77)
+    ids = torch.randperm(50_000, generator=torch.Generator().manual_seed(2))[:n] + 1
+    sc_all = bf16_round(q) @ bf16_round(it).t()
+    excl = torch.full((nq, 30), -1, dtype=torch.int64)
+    for r in range(nq):
+        excl[r, :25] = ids[sc_all[r].topk(25).indices]           # the 25 best of every query are excluded
+        excl[r, 25:28] = torch.tensor([60_001, 60_002, 60_003])  # ids that are not in the catalog
+    index = xfmr_b200.ItemProcessor(metric="dot", compute="bf16").get_index(it.bfloat16(), ids)
+    scores, got = index.search_batch(q.bfloat16(), excl, top_k=k)
+    got_c = got.cpu()
+    assert not bool((got_c[:, :, None] == excl[:, None, :]).any())
+    allowed = ~(ids[None, :, None] == excl[:, None, :]).any(dim=2)
+    sc, must, kth = _brute_force_must_have(q.cuda().bfloat16(), it.cuda().bfloat16(), k, allowed.cuda())
+    pos = {int(v): j for j, v in enumerate(ids.tolist())}
+    cols = torch.tensor([[pos[int(v)] for v in row] for row in got_c.tolist()], device="cuda")
+    returned = torch.zeros_like(must)
+    returned.scatter_(1, cols, True)
+    assert bool((returned | ~must).all())
+    assert bool((sc.gather(1, cols) >= kth - 2e-6).all())
