@@ -1234,13 +1234,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             }
           };
           if constexpr (!MINING) {
-            float m0 = fmaxf(__uint_as_float(s[0]), fmaxf(__uint_as_float(s[1]), __uint_as_float(s[2])));
-            float m1 = fmaxf(__uint_as_float(s[3]), fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5])));
-            float m2 = fmaxf(__uint_as_float(s[6]), fmaxf(__uint_as_float(s[7]), __uint_as_float(s[8])));
-            float m3 = fmaxf(__uint_as_float(s[9]), fmaxf(__uint_as_float(s[10]), __uint_as_float(s[11])));
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[12]), __uint_as_float(s[13])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(s[14]), __uint_as_float(s[15])));
-            const bool hit = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr_f;
+            const float m0 = fmax3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+            const float m1 = fmax3(__uint_as_float(s[3]), __uint_as_float(s[4]), __uint_as_float(s[5]));
+            const float m2 = fmax3(__uint_as_float(s[6]), __uint_as_float(s[7]), __uint_as_float(s[8]));
+            const float m3 = fmax3(__uint_as_float(s[9]), __uint_as_float(s[10]), __uint_as_float(s[11]));
+            const float m4 = fmax3(__uint_as_float(s[12]), __uint_as_float(s[13]), __uint_as_float(s[14]));
+            const bool hit = fmax3(fmax3(m0, m1, m2), fmax3(m3, m4, __uint_as_float(s[15])), -INFINITY) >= thr_f;
             if (__ballot_sync(0xffffffffu, hit)) {
               // Every lane parks its 16 words in shared memory (dynamic indexing), builds the bit mask of its passing
               // columns and appends them to its OWN row's buffer: no shuffles, and the cost does not grow with the

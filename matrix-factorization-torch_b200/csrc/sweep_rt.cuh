@@ -280,12 +280,13 @@ rt_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUten
         auto select_unit = [&](const uint32_t (&s)[32], uint32_t mu, uint32_t c0) __attribute__((always_inline)) {
           // one max tree and one vote per 32 scores; a unit in which some row can beat its current threshold takes the
           // append path: the rows with a hit go one at a time through a 32-word shared-memory slot (dynamic indexing)
-          float m[8];
+          // (16 three-input maxima for 32 scores)
+          float m[10];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            m[i] = fmaxf(fmaxf(__uint_as_float(s[4 * i]), __uint_as_float(s[4 * i + 1])),
-                         fmaxf(__uint_as_float(s[4 * i + 2]), __uint_as_float(s[4 * i + 3])));
-          const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+          for (int i = 0; i < 10; ++i)
+            m[i] = fmax3(__uint_as_float(s[3 * i]), __uint_as_float(s[3 * i + 1]), __uint_as_float(s[3 * i + 2]));
+          const float mx = fmaxf(fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmax3(m[6], m[7], m[8])),
+                                 fmax3(m[9], __uint_as_float(s[30]), __uint_as_float(s[31])));
           const bool hit = mx >= thr_f;
           if (__ballot_sync(0xffffffffu, hit) == 0u) return;
           uint32_t pm = 0u;
