@@ -391,18 +391,7 @@ static int build_pair_mask(int nrows, int ncols, int list_len, const long long* 
 // ------------------------------------------------------------------------------------------------
 // Loss workspace
 // ------------------------------------------------------------------------------------------------
-constexpr int MINE_CAP = 256;    // largest candidate buffer per row for the mining sweep (workspace is sized for it)
-// actual buffer for a given number of kept entries
-static int mine_cap_for(int keep) {
-  static const int forced = [] {
-    const char* e = std::getenv("XB_MINE_CAP");
-    return e != nullptr ? atoi(e) : 0;
-  }();
-  if (forced >= 64 && forced <= MINE_CAP && (forced & (forced - 1)) == 0 && forced >= 2 * keep) return forced;
-  int cap = 64;
-  while (cap < 4 * keep + 32) cap <<= 1;   // (measured at config 2, keep = 20: 128 -> 1.66 ms/step, 256 -> 1.69, 64 -> 1.90)
-  return cap < MINE_CAP ? cap : MINE_CAP;
-}
+constexpr int MINE_CAP = 256;    // candidate buffer per mining stream: what a compaction keeps (<= 100) + a whole tile of appends (128)
 constexpr int MINE_KMAX = 64;    // largest supported num_negatives
 // Extra candidates per side that are re-scored exactly (fp64) before the final selection.  The sweep ranks by tensor-core
 // scores; a column can only change places with the K-th best if its exact key lies within the score error of it.  bf16
@@ -953,7 +942,12 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
       p.rpar = reinterpret_cast<float*>(ws + w.qmine);
       p.cand = reinterpret_cast<unsigned long long*>(ws + w.cand);
       p.cand_cnt = reinterpret_cast<int*>(ws + w.cand_cnt);
-      p.cap = mine_cap_for(w.Kf);
+      static const int trigger_env = [] {
+        const char* e = std::getenv("XB_MINE_TRIGGER");
+        return e != nullptr ? atoi(e) : 0;
+      }();
+      p.mine_trigger = (trigger_env >= w.Kf + (w.Kf >> 2) && trigger_env <= MINE_CAP - BN) ? trigger_env : MINE_CAP - BN;
+      p.cap = MINE_CAP;   // a buffer takes a whole tile from both column parts (<= 128 entries) on top of what a compaction keeps
       p.keep = w.Kf;
       const bool hard = desc->mining == XB_MINING_HARD;
       // hard mining has one continuous order (logit descending): one sweep; the second half of `sel` stays empty
@@ -965,7 +959,7 @@ int xb_loss_forward(const xb_loss_desc* desc, const void* user_embed, const void
         const char* e = std::getenv("XB_MINE_SWEEPS");
         return e != nullptr && e[0] == '2';
       }();
-      const int nstreams = w.fwd.nchunks * epi_parts(MODE_TOPK, 1, true);
+      const int nstreams = w.fwd.nchunks;   // one stream per row, side and column chunk (shared by the column parts)
       const long long side_rows = static_cast<long long>(nstreams) * p.nR_pad;
       if (hard || two_sweeps) {
         for (int side = 0; side < (hard ? 1 : 2); ++side) {

@@ -123,6 +123,7 @@ struct SweepParams {
                              // 4: BOTH 1 and 2 in one pass: every row keeps two candidate streams; the second one lives
                              //    `cand_side` streams behind the first in cand / cand_cnt
   long long cand_side;       // mode 4: rows (= streams) per side in cand / cand_cnt
+  int mine_trigger;          // mining: a stream is compacted at a tile end once it holds more entries than this (<= cap - 128)
   // GRAD, item-major sweep of an exponential loss (see grad_fold_kernel): the column operand is the sign-folded
   // query tile and its aug block carries the per-query offset, so x_ij = cabs * T_ij - lq2_i and |G_ij| = 2^x_ij
   float cabs;                // |sigma| * log2(e)
@@ -155,6 +156,7 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int kp, int parts, 
   L.bar_off = L.par_off + par_bytes;
   L.stage_off = L.bar_off + 256u;  // barriers + tmem pointer
   L.total = L.stage_off + static_cast<uint32_t>(topk_warps) * 32u * TOPK_STAGE_STRIDE * 4u;
+  if (topk_warps > 0) L.total += 4u * BM * 4u;   // mining: shared stream state of the 128 rows (count and threshold, two sides)
   return L;
 }
 
@@ -906,8 +908,26 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // three packed FMAs per element pair and one funnel shift per element that collects the sign bits of d: no min
     // tree, no separate vote, no per-shape branches.  The window carries a rounding slack; the exact key decides below.
     float wb = 0.f, wq = 0.f, wl = 0.f, wc = -1.f;
-    int cntB = 0;
     uint32_t thrB = row_ok ? 0u : 0xffffffffu;
+    // Mining streams are shared by the two column parts of a row (warps w and w + 4): ONE stream per row, side and column
+    // chunk - half the streams means half the admissions, since a stream of n columns admits ~keep ln(n / keep) whatever
+    // n is.  Counts and thresholds live in shared memory (appends claim a slot with an atomic add; `thr` / `thrB` are
+    // this thread's copies, refreshed once per tile), compactions run at tile ends between two barriers of the pair.
+    uint32_t* sCntA = sStage + 4 * EP * 32 * TOPK_STAGE_STRIDE;
+    uint32_t* sCntB = sCntA + BM;
+    uint32_t* sThrA = sCntB + BM;
+    uint32_t* sThrB = sThrA + BM;
+    const size_t mine_row = static_cast<size_t>(chunk) * p.nR_pad + row;   // stream index (side A; side B is cand_side further)
+    if constexpr (MODE == MODE_TOPK && LM != 0) {
+      named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);       // the partner is done with the previous row block
+      if (part == 0) {
+        sCntA[row_l] = 0u;
+        sCntB[row_l] = 0u;
+        sThrA[row_l] = thr;
+        sThrB[row_l] = thrB;
+      }
+      named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);
+    }
     // interval [lo, hi] of R whose keys lie above threshold `t` of a stream (mirrored: the stream orders -R)
     auto key_window = [&](uint32_t t, bool mirrored, float& lo, float& hi) {
       if (t == 0xffffffffu) { lo = INFINITY; hi = -INFINITY; return; }     // dead row: empty
@@ -1200,36 +1220,24 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           // compaction: a row whose buffer cannot absorb another 16 candidates is reduced by its warp to the best
           // `keep` entries; the keep-th best becomes the admission threshold (equal keys stay eligible: the lower
           // column wins ties).
-          // (mining mode 4: the same for the mirrored stream of each row - one loop over the sides, so that the bit search
-          //  and the window update are inlined once per unit copy)
+          // (retrieval only: the mining streams are compacted at tile ends, see below)
           auto compact_full_rows = [&]() {
-            constexpr int nsides = (MINING && MINE == 4) ? 2 : 1;
-            for (int side = 0; side < nsides; ++side) {
-              const int mycnt = side ? cntB : cnt;
-              uint32_t need = __ballot_sync(0xffffffffu, mycnt > p.cap - 16);
-              while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                unsigned long long* buf = p.cand + (side * p.cand_side + out_row - lane + src) * p.cap;
-                const int n = __shfl_sync(0xffffffffu, mycnt, src);
-                __syncwarp();
-                int kept = p.keep;
-                // (a quarter more than `keep` may survive: the bit search then stops about half-way)
-                const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
-                __syncwarp();
-                if (lane == src) {
-                  const uint32_t kk = static_cast<uint32_t>(kth >> 32);
-                  const uint32_t nthr = kk > 0 ? kk - 1 : 0;
-                  if (side) {
-                    cntB = kept;
-                    thrB = nthr;
-                  } else {
-                    cnt = kept;
-                    thr = nthr;
-                    thr_f = order_key_inv(kk);
-                  }
-                  if (MINING) set_window();
-                }
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > p.cap - 16);
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              unsigned long long* buf = p.cand + (out_row - lane + src) * p.cap;
+              const int n = __shfl_sync(0xffffffffu, cnt, src);
+              __syncwarp();
+              int kept = p.keep;
+              // (a quarter more than `keep` may survive: the bit search then stops about half-way)
+              const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
+              __syncwarp();
+              if (lane == src) {
+                cnt = kept;
+                const uint32_t kk = static_cast<uint32_t>(kth >> 32);
+                thr = kk > 0 ? kk - 1 : 0;
+                thr_f = order_key_inv(kk);
               }
             }
           };
@@ -1288,7 +1296,6 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
               }
               pm = (__brev(~pm) >> 16) & ~mu;                        // element c at bit c; set <=> d >= 0 (or NaN)
             }
-            constexpr bool hard_order = MINE == 3;
             const bool any = __ballot_sync(0xffffffffu, pm != 0u) != 0u;
             if (any) {
               if (pm) {
@@ -1307,6 +1314,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                   }
                   float r = l2 + rp_reg[2];                          // rp_reg[2] = -L2_ii: R = L_ij - L_ii
                   const uint32_t ent_lo = static_cast<uint32_t>(~(col0 + static_cast<uint32_t>(c)));
+                  unsigned long long* cbA = p.cand + mine_row * p.cap;
                   if (MINE == 4) {
                     // both orders from one score: the reference order on R, the mirror image on -R (an exact 0 belongs to
                     // BOTH first groups: -0 -> +0 on the first side, 0 -> -0 on the mirrored one)
@@ -1315,8 +1323,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                     uint32_t ka = __float_as_uint(ra) ^ 0x7fffffffu, km = __float_as_uint(rm) ^ 0x7fffffffu;
                     ka = (r != r) ? 1u : max(ka, 1u);
                     km = (r != r) ? 1u : max(km, 1u);
-                    if (ka > thr) cb[cnt++] = (static_cast<unsigned long long>(ka) << 32) | ent_lo;
-                    if (km > thrB) cb[p.cand_side * p.cap + cntB++] = (static_cast<unsigned long long>(km) << 32) | ent_lo;
+                    if (ka > thr) cbA[atomicAdd(&sCntA[row_l], 1u)] = (static_cast<unsigned long long>(ka) << 32) | ent_lo;
+                    if (km > thrB)
+                      cbA[p.cand_side * p.cap + atomicAdd(&sCntB[row_l], 1u)] = (static_cast<unsigned long long>(km) << 32) | ent_lo;
                     continue;
                   }
                   if (MINE == 2) {
@@ -1324,13 +1333,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                   } else {
                     r += 0.0f;                                       // -0 -> +0 (losses.py:149 tests `< 0`)
                   }
-                  uint32_t kk = hard_order ? order_key(r) : (__float_as_uint(r) ^ 0x7fffffffu);
+                  uint32_t kk = (MINE == 3) ? order_key(r) : (__float_as_uint(r) ^ 0x7fffffffu);
                   kk = (r != r) ? 1u : max(kk, 1u);
-                  if (kk > thr) cb[cnt++] = (static_cast<unsigned long long>(kk) << 32) | ent_lo;
+                  if (kk > thr) cbA[atomicAdd(&sCntA[row_l], 1u)] = (static_cast<unsigned long long>(kk) << 32) | ent_lo;
                 }
               }
               __syncwarp();
-              compact_full_rows();
             }
           }
         }
@@ -1341,6 +1349,41 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       for (int k = 0; k < UPT; k += 2) {
         do_unit(va, vb, k);
         do_unit(vb, va, k + 1);
+      }
+      if constexpr (MODE == MODE_TOPK && LM != 0) {
+        // Mining, end of a tile: a buffer must be able to take a whole tile from both parts (<= 128 entries per side), so
+        // rows above cap - 128 are compacted now - side A by the part-0 warp of the pair, side B by its partner.
+        named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);     // every append of this tile is in the buffers
+        if (part == 0 || MINE == 4) {
+          const int side = part;
+          uint32_t* cnt_s = side ? sCntB : sCntA;
+          uint32_t* thr_s = side ? sThrB : sThrA;
+          const int mycnt = static_cast<int>(cnt_s[row_l]);
+          uint32_t need = __ballot_sync(0xffffffffu, mycnt > p.mine_trigger);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            unsigned long long* buf = p.cand + (side * p.cand_side + mine_row - lane + src) * p.cap;
+            const int n = __shfl_sync(0xffffffffu, mycnt, src);
+            __syncwarp();
+            int kept = p.keep;
+            // (a quarter more than `keep` may survive: the bit search then stops about half-way)
+            const unsigned long long kth = compact_dispatch(buf, n, p.cap, p.keep, lane, p.keep >> 2, &kept);
+            __syncwarp();
+            if (lane == src) {
+              const uint32_t kk = static_cast<uint32_t>(kth >> 32);
+              cnt_s[row_l] = static_cast<uint32_t>(kept);
+              thr_s[row_l] = kk > 0 ? kk - 1 : 0;
+            }
+          }
+        }
+        named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);     // thresholds of both sides are final for the next tile
+        const uint32_t tA = sThrA[row_l], tB = sThrB[row_l];
+        if (tA != thr || tB != thrB) {
+          thr = tA;
+          thrB = tB;
+          set_window();
+        }
       }
       if (tr) p.trace[t * 8 + 5] = clock64();
       if (HAS_G) {
@@ -1467,8 +1510,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if (!FWDQ) *reinterpret_cast<float2*>(p.out_stats + out_row * 2) = make_float2(rg, rgh);
     }
     if (MODE == MODE_TOPK) {
-      p.cand_cnt[out_row] = cnt;
-      if (LM != 0 && MINE == 4) p.cand_cnt[p.cand_side + out_row] = cntB;
+      if constexpr (LM != 0) {
+        if (part == 0) {
+          p.cand_cnt[mine_row] = static_cast<int>(sCntA[row_l]);
+          if (MINE == 4) p.cand_cnt[p.cand_side + mine_row] = static_cast<int>(sCntB[row_l]);
+        }
+      } else {
+        p.cand_cnt[out_row] = cnt;
+      }
     }
     if (HAS_G && more_blocks) {
       // the accumulator is in registers / memory: the second MMA of the next row block may overwrite it
