@@ -71,7 +71,8 @@ enum : int { LM_CONTR = 1, LM_INFONCE = 2, LM_MINE = 4, LM_HINGE = 8, LM_LOGI = 
 __host__ __device__ constexpr bool lm_single(int lm) { return (lm & (lm - 1)) == 0; }
 // number of epilogue column parts of a kernel variant
 __host__ __device__ constexpr int epi_parts(int mode, int lm, bool /*qrow*/) {
-  // (TOPK with 4 parts was measured: the 104-register cap of a 608-thread CTA spills the selection state, 3x slower)
+  // (TOPK with 4 parts was measured twice: the 96-register cap of a 608-thread CTA spills - 3x slower for retrieval in
+  //  round 1, and worse for mining in round 2 even with the selection state in shared memory: 248 bytes of stack)
   return ((mode == 0 /*FWD*/ || mode == 1 /*GRAD*/ || mode == 4 /*FWDQ*/) && lm != 0 && lm_single(lm)) ? 4 : 2;
 }
 // threads per CTA: epilogue warps + TMA producer warp + two MMA issuer warps
@@ -919,14 +920,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     uint32_t* sThrB = sThrA + BM;
     const size_t mine_row = static_cast<size_t>(chunk) * p.nR_pad + row;   // stream index (side A; side B is cand_side further)
     if constexpr (MODE == MODE_TOPK && LM != 0) {
-      named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);       // the partner is done with the previous row block
+      named_bar_sync(8u + static_cast<uint32_t>(quad), 32u * EP);       // the partner is done with the previous row block
       if (part == 0) {
         sCntA[row_l] = 0u;
         sCntB[row_l] = 0u;
         sThrA[row_l] = thr;
         sThrB[row_l] = thrB;
       }
-      named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);
+      named_bar_sync(8u + static_cast<uint32_t>(quad), 32u * EP);
     }
     // interval [lo, hi] of R whose keys lie above threshold `t` of a stream (mirrored: the stream orders -R)
     auto key_window = [&](uint32_t t, bool mirrored, float& lo, float& hi) {
@@ -1353,7 +1354,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       if constexpr (MODE == MODE_TOPK && LM != 0) {
         // Mining, end of a tile: a buffer must be able to take a whole tile from both parts (<= 128 entries per side), so
         // rows above cap - 128 are compacted now - side A by the part-0 warp of the pair, side B by its partner.
-        named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);     // every append of this tile is in the buffers
+        named_bar_sync(8u + static_cast<uint32_t>(quad), 32u * EP);     // every append of this tile is in the buffers
         if (part == 0 || MINE == 4) {
           const int side = part;
           uint32_t* cnt_s = side ? sCntB : sCntA;
@@ -1377,7 +1378,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             }
           }
         }
-        named_bar_sync(8u + static_cast<uint32_t>(quad), 64u);     // thresholds of both sides are final for the next tile
+        named_bar_sync(8u + static_cast<uint32_t>(quad), 32u * EP);     // thresholds of both sides are final for the next tile
         const uint32_t tA = sThrA[row_l], tB = sThrB[row_l];
         if (tA != thr || tB != thrB) {
           thr = tA;
