@@ -484,9 +484,9 @@ static bool loss_ws_layout(const xb_loss_desc* d, LossWs* w) {
   w->rsi = take(sizeof(float) * 2 * static_cast<size_t>(ni) * MAX_EPI_PARTS * w->N_pad);
   w->gdiag = take(sizeof(float) * B);
   if (w->mining) {
-    // two candidate streams per (row, sub-chunk): the reference order and its mirror image, filled by ONE sweep
-    w->cand = take(sizeof(unsigned long long) * 2 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad * MINE_CAP);
-    w->cand_cnt = take(sizeof(int) * 2 * static_cast<size_t>(w->fwd.nchunks) * MAX_EPI_PARTS * w->B_pad);
+    // two candidate streams per (row, column chunk): the reference order and its mirror image, filled by ONE sweep
+    w->cand = take(sizeof(unsigned long long) * 2 * static_cast<size_t>(w->fwd.nchunks) * w->B_pad * MINE_CAP);
+    w->cand_cnt = take(sizeof(int) * 2 * static_cast<size_t>(w->fwd.nchunks) * w->B_pad);
     w->sel = take(sizeof(unsigned long long) * static_cast<size_t>(B) * 2 * w->Kf);
     w->selcol = take(sizeof(int) * static_cast<size_t>(B) * w->K);
     w->selL2 = take(sizeof(float) * static_cast<size_t>(B) * w->K);
