@@ -1272,10 +1272,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             }
           } else {
             // Mining.  The exact key is bits(R) ^ 0x7fffffff with R = L_ij - L_ii (semi-hard R<0 by R desc, then hard by
-            // R asc; mode 2 mirrors the order, mode 3 = hard mining orders by R desc).  Keys above the threshold form a
-            // WINDOW of R (see set_window), so the vote needs one FMA per element, u = R - window centre, and a min
-            // tree over |u| (mode 3: a max tree over u); the window is conservative, the exact key decides below.
-            // candidate bits of the unit: sign bits of the window quadratic (see set_window)
+            // R asc; MINE 2 mirrors the order, MINE 3 = hard mining orders by R desc, MINE 4 keeps both orders).  Keys above
+            // a threshold form a WINDOW of R; the candidate bits of the unit are the sign bits of the window quadratic (see
+            // set_window): conservative, the exact key decides below.
             uint32_t pm = 0u;
             {
               const float a2 = rp_reg[0];
