@@ -900,6 +900,47 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
   }
 }
 
+// Single-chunk variant of grad_finalize_i_kernel (the sparse path of mining and the alignment-only call: one fp32
+// accumulator row per item, d % 4 == 0): a warp finishes FOUR rows, every load of the four issued before the first use -
+// the one-row-per-warp kernel is latency-bound at 24 bytes in flight per thread (1.5 TB/s on 73 MB at config 2).
+template <typename T>
+__global__ void __launch_bounds__(256) grad_finalize_i_rows4_kernel(int N, int B, int d, int kp, int parts,
+                                                                    const float* __restrict__ acc,
+                                                                    const float* __restrict__ rs_part,
+                                                                    const __nv_bfloat16* __restrict__ ip,
+                                                                    const __nv_bfloat16* __restrict__ qp,
+                                                                    const float* __restrict__ gdiag, T* __restrict__ di) {
+  const int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= N) return;
+  float cg[4], gjj[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = min(row0 + r, N - 1);
+    cg[r] = rs_part[static_cast<size_t>(row) * 2];
+    gjj[r] = row < B ? gdiag[row] : 0.f;
+  }
+  for (int k = lane * 4; k < d; k += 128) {
+    float4 a[4], vv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = min(row0 + r, N - 1);
+      a[r] = *reinterpret_cast<const float4*>(acc + static_cast<size_t>(row) * kp + k);
+      vv[r] = prepped_val4(ip + static_cast<size_t>(row) * parts * kp, kp, parts, k);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = row0 + r;
+      if (row >= N) break;
+      float4 qv = vv[r];                           // (q - v) = 0 outside the in-batch block
+      if (row < B) qv = prepped_val4(qp + static_cast<size_t>(row) * parts * kp, kp, parts, k);
+      store_out4<T>(di + static_cast<size_t>(row) * d + k,
+                    make_float4(a[r].x - cg[r] * vv[r].x + gjj[r] * (qv.x - vv[r].x), a[r].y - cg[r] * vv[r].y + gjj[r] * (qv.y - vv[r].y),
+                                a[r].z - cg[r] * vv[r].z + gjj[r] * (qv.z - vv[r].z), a[r].w - cg[r] * vv[r].w + gjj[r] * (qv.w - vv[r].w)));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Candidate-list finalisation (top-k and mining): merge the per-chunk buffers of a row, sort by
 // (key desc, column asc) and emit the first k entries.  One warp per row; total entries <= 1024.
@@ -933,7 +974,7 @@ __global__ void __launch_bounds__(128) cand_finalize_kernel(int nrows, int nR_pa
     while (done < n) {
       if (cnt + min(n - done, 512) > CANDF_STAGE) {
         __syncwarp();
-        compact_select<32>(st, cnt, k, lane);
+        compact_dispatch(st, cnt, cnt <= 64 ? 64 : cnt <= 128 ? 128 : cnt <= 256 ? 256 : cnt <= 512 ? 512 : 1024, k, lane, 0, nullptr);
         cnt = min(cnt, k);
         __syncwarp();
       }
@@ -945,7 +986,8 @@ __global__ void __launch_bounds__(128) cand_finalize_kernel(int nrows, int nR_pa
   }
   __syncwarp();
   if (cnt > k) {
-    compact_select<32>(st, cnt, k, lane);
+    // (the select works on a power-of-two number of slots per lane: pick the smallest that holds the entries)
+    compact_dispatch(st, cnt, cnt <= 64 ? 64 : cnt <= 128 ? 128 : cnt <= 256 ? 256 : cnt <= 512 ? 512 : 1024, k, lane, 0, nullptr);
     cnt = k;
     __syncwarp();
   }
@@ -1265,15 +1307,20 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
       if ((s0 >> 5) == t) { key_[t] = key; col_[t] = col; l2_[t] = l2; }
   }
   __syncwarp();
-  // phase 2a: drop the later copy of a column that both candidate lists delivered
+  // phase 2a: drop the later copy of a column that both candidate lists delivered.  (Loops over the lanes stay rolled and
+  // stop at the slots in use: unrolled for 5 slots x 32 lanes this kernel was instruction-fetch-bound - 20 stall cycles
+  // per issued instruction for code every warp runs exactly once.)
+  const int nslots = (Kf + 31) >> 5;
 #pragma unroll
   for (int tt = 0; tt < MINE_SLOTS; ++tt) {
+    if (tt >= nslots) break;
+#pragma unroll 1
     for (int src = 0; src < 32; ++src) {
       const int oc = __shfl_sync(0xffffffffu, col_[tt], src);
       if (oc < 0) continue;  // warp-uniform
 #pragma unroll
       for (int t = 0; t < MINE_SLOTS; ++t)
-        if (oc == col_[t] && tt * 32 + src < t * 32 + lane) key_[t] = 0ull;
+        if (t < nslots && oc == col_[t] && tt * 32 + src < t * 32 + lane) key_[t] = 0ull;
     }
   }
   // phase 2b: rank = number of candidates ordered before this one (key desc, column asc)
@@ -1282,13 +1329,15 @@ __global__ void mined_forward_kernel(int B, int K, int Kf, int d, int kp, int pa
   for (int t = 0; t < MINE_SLOTS; ++t) rank_[t] = 0;
 #pragma unroll
   for (int tt = 0; tt < MINE_SLOTS; ++tt) {
+    if (tt >= nslots) break;
+#pragma unroll 1
     for (int src = 0; src < 32; ++src) {
       const unsigned long long ok = __shfl_sync(0xffffffffu, key_[tt], src);
       const int oc = __shfl_sync(0xffffffffu, col_[tt], src);
       if (ok == 0ull) continue;  // warp-uniform
 #pragma unroll
       for (int t = 0; t < MINE_SLOTS; ++t)
-        rank_[t] += (ok > key_[t] || (ok == key_[t] && oc < col_[t])) ? 1 : 0;
+        if (t < nslots) rank_[t] += (ok > key_[t] || (ok == key_[t] && oc < col_[t])) ? 1 : 0;
     }
   }
   for (int pos = lane; pos < K; pos += 32) selcol[static_cast<size_t>(row) * K + pos] = -1;
