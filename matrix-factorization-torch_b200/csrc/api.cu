@@ -736,8 +736,12 @@ static int loss_backward_typed(const xb_loss_desc* desc, const LossWs& w, const 
   if (!q_guard.join()) return fail(XB_ERR_CUDA, "stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (wg_items) {
     const long long vrows = static_cast<long long>(w.B_pad / BM + w.wi.grid - 1) * BM;
-    grad_finalize_i_kernel<T><<<cdiv(vrows * 32, 256), 256, 0, st>>>(N, B, d, w.kp, w.parts, w.N_pad, 1, 1, acci, rsi, iprep, qprep,
-                                                                    gdiag, di, w.wi.tb, w.wi.W, w.B_pad / BM);
+    if ((d & 3) == 0)
+      grad_finalize_i_wg2_kernel<T><<<cdiv(vrows / 2 * 32, 256), 256, 0, st>>>(N, B, d, w.kp, w.parts, w.N_pad, acci, rsi, iprep, qprep,
+                                                                              gdiag, di, w.wi.tb, w.wi.W, w.B_pad / BM);
+    else
+      grad_finalize_i_kernel<T><<<cdiv(vrows * 32, 256), 256, 0, st>>>(N, B, d, w.kp, w.parts, w.N_pad, 1, 1, acci, rsi, iprep, qprep,
+                                                                      gdiag, di, w.wi.tb, w.wi.W, w.B_pad / BM);
   } else if (ni == 1 && ni_sub == 1 && (d & 3) == 0) {
     grad_finalize_i_rows4_kernel<T><<<cdiv(static_cast<long long>(cdiv(n_final_rows, 4)) * 32, 256), 256, 0, st>>>(
         n_final_rows, B, d, w.kp, w.parts, acci, rsi, iprep, qprep, gdiag, di);

@@ -900,6 +900,61 @@ __global__ void grad_finalize_i_kernel(int N, int B, int d, int kp, int parts, i
   }
 }
 
+// Piece-aware variant for the warpgroup-per-tile dI sweep (the wg_w > 0 branch of grad_finalize_i_kernel, d % 4 == 0): a warp
+// finishes TWO rows of the same virtual block (r and r + 64: same row block, same pieces), all loads of both issued first.
+template <typename T>
+__global__ void __launch_bounds__(256) grad_finalize_i_wg2_kernel(int N, int B, int d, int kp, int parts, int nR_pad,
+                                                                  const float* __restrict__ acc,
+                                                                  const float* __restrict__ rs_part,
+                                                                  const __nv_bfloat16* __restrict__ ip,
+                                                                  const __nv_bfloat16* __restrict__ qp,
+                                                                  const float* __restrict__ gdiag, T* __restrict__ di,
+                                                                  int wg_tb, int wg_w, int wg_rb0) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp -> (virtual block v, row pair r)
+  const int lane = threadIdx.x & 31;
+  const int v = gw / (BM / 2), r = gw % (BM / 2);
+  int rb = v;
+  if (v >= wg_rb0) {   // (same mapping as grad_finalize_i_kernel)
+    const long long lin = static_cast<long long>(v - wg_rb0 + 1) * wg_w;
+    rb = static_cast<int>(lin / wg_tb);
+    if (lin % wg_tb == 0 || rb < wg_rb0) return;
+    if (static_cast<long long>(v - wg_rb0) * wg_w > static_cast<long long>(rb) * wg_tb) return;
+  }
+  const int rows[2] = {rb * BM + r, rb * BM + r + BM / 2};
+  if (rows[0] >= N) return;
+  const int np = wg_pieces(rb, wg_tb, wg_w);
+  float cg[2] = {0.f, 0.f}, gjj[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int row = min(rows[j], N - 1);
+    for (int c = 0; c < np; ++c) cg[j] += rs_part[(static_cast<size_t>(c) * nR_pad + row) * 2];
+    gjj[j] = row < B ? gdiag[row] : 0.f;
+  }
+  for (int k = lane * 4; k < d; k += 128) {
+    float4 s[2], vv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = min(rows[j], N - 1);
+      s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < np; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(acc + (static_cast<size_t>(c) * nR_pad + row) * kp + k);
+        s[j].x += x.x; s[j].y += x.y; s[j].z += x.z; s[j].w += x.w;
+      }
+      vv[j] = prepped_val4(ip + static_cast<size_t>(row) * parts * kp, kp, parts, k);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = rows[j];
+      if (row >= N) break;
+      float4 qv = vv[j];
+      if (row < B) qv = prepped_val4(qp + static_cast<size_t>(row) * parts * kp, kp, parts, k);
+      store_out4<T>(di + static_cast<size_t>(row) * d + k,
+                    make_float4(s[j].x - cg[j] * vv[j].x + gjj[j] * (qv.x - vv[j].x), s[j].y - cg[j] * vv[j].y + gjj[j] * (qv.y - vv[j].y),
+                                s[j].z - cg[j] * vv[j].z + gjj[j] * (qv.z - vv[j].z), s[j].w - cg[j] * vv[j].w + gjj[j] * (qv.w - vv[j].w)));
+    }
+  }
+}
+
 // Single-chunk variant of grad_finalize_i_kernel (the sparse path of mining and the alignment-only call: one fp32
 // accumulator row per item, d % 4 == 0): a warp finishes FOUR rows, every load of the four issued before the first use -
 // the one-row-per-warp kernel is latency-bound at 24 bytes in flight per thread (1.5 TB/s on 73 MB at config 2).
