@@ -1354,9 +1354,14 @@ int xb_topk_merge(int32_t num_queries, int32_t num_lists, int32_t list_len, int3
   fill_topk_empty_kernel<<<cdiv(static_cast<long long>(num_queries) * k, 256), 256, 0, st>>>(
       static_cast<size_t>(num_queries) * k, scores_out, reinterpret_cast<long long*>(ids_out));
   XB_LAUNCHED();
-  pairs_select_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
-      num_queries, num_lists * list_len, k, in_scores, reinterpret_cast<const long long*>(in_ids), scores_out,
-      reinterpret_cast<long long*>(ids_out));
+  if (static_cast<long long>(num_lists) * list_len <= PAIRS_LMAX)
+    pairs_select_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
+        num_queries, num_lists * list_len, k, in_scores, reinterpret_cast<const long long*>(in_ids), scores_out,
+        reinterpret_cast<long long*>(ids_out));
+  else
+    pairs_select_allpairs_kernel<<<cdiv(static_cast<long long>(num_queries) * 32, 128), 128, 0, st>>>(
+        num_queries, num_lists * list_len, k, in_scores, reinterpret_cast<const long long*>(in_ids), scores_out,
+        reinterpret_cast<long long*>(ids_out));
   XB_LAUNCHED();
   return XB_OK;
 }

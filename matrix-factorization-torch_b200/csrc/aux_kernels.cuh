@@ -1098,19 +1098,91 @@ __global__ void topk_rescore_kernel(int Q, int k, int d, const unsigned long lon
   ids_tmp[g] = item_ids != nullptr ? item_ids[col] : id_base + col;
 }
 
-// final ordering by (score desc, id asc) of L <= 1024 (score, id) pairs per row; emits the best k.
-// One warp per row.  Ids are compared as full int64 through a two-key sort: entries are ranked by a
-// 64-bit (score key, slot) sort after a stable pre-ordering by id is folded into the slot tie-break.
-__global__ void pairs_select_kernel(int Q, int L, int k, const float* __restrict__ scores,
-                                    const long long* __restrict__ ids, float* __restrict__ scores_out,
-                                    long long* __restrict__ ids_out) {
+// final ordering by (score desc, id asc, slot asc) of L <= 1024 (score, id) pairs per row; emits the best k.
+// One warp per row, two steps: (1) the k-th largest score key of the row by a 32-round bit search over the keys staged in
+// shared memory - L / 32 compares per lane and round; (2) only the survivors (key >= that threshold: k of them plus ties)
+// are ranked against each other, ids fetched for equal keys only.  The plain all-pairs ranking it replaces is O(L^2 / 32)
+// global loads per lane: 20,000 at L = 800 (the merge of eight shards' top-100 lists), 4.9 ms per rank at config 5.
+constexpr int PAIRS_LMAX = 1024;
+__global__ void __launch_bounds__(128) pairs_select_kernel(int Q, int L, int k, const float* __restrict__ scores,
+                                                           const long long* __restrict__ ids, float* __restrict__ scores_out,
+                                                           long long* __restrict__ ids_out) {
+  __shared__ uint32_t s_key[4][PAIRS_LMAX];
+  __shared__ uint16_t s_idx[4][PAIRS_LMAX];
+  const int wib = threadIdx.x >> 5;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= Q) return;
   const float* s = scores + static_cast<size_t>(row) * L;
   const long long* id = ids + static_cast<size_t>(row) * L;
-  // rank of an entry = number of entries that precede it in (score desc, id asc, slot asc) order.
-  // L is small (<= 1024): O(L^2 / 32) comparisons per lane is a few thousand.
+  uint32_t* key = s_key[wib];
+  uint16_t* sidx = s_idx[wib];
+  // keys: order_key(score) >= 1 for a valid entry, 0 for an empty slot (id < 0)
+  int valid = 0;
+  for (int i = lane; i < L; i += 32) {
+    const bool ok = id[i] >= 0;
+    key[i] = ok ? max(order_key(s[i]), 1u) : 0u;
+    valid += ok ? 1 : 0;
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  __syncwarp();
+  // (1) T = the k-th largest key (1 if the row holds at most k valid entries: everything survives)
+  uint32_t T = 1u;
+  if (valid > k) {
+    T = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < L; i += 32) c += key[i] >= cand ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) T = cand;   // (warp-uniform)
+    }
+  }
+  // (2) survivors, in slot order
+  int m = 0;
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const bool keep = i < L && key[i] >= T;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) sidx[m + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+    m += __popc(bal);
+  }
+  __syncwarp();
+  for (int a = lane; a < m; a += 32) {
+    const int i = sidx[a];
+    const uint32_t ki = key[i];
+    long long idi = 0;
+    bool have_id = false;
+    int rank = 0;
+    for (int b = 0; b < m; ++b) {
+      const int j = sidx[b];
+      const uint32_t kj = key[j];
+      if (kj > ki) {
+        ++rank;
+      } else if (kj == ki && j != i) {
+        // equal scores: (id asc, slot asc) decides (rare: ids come from global memory only here)
+        if (!have_id) { idi = id[i]; have_id = true; }
+        const long long idj = id[j];
+        rank += (idj < idi || (idj == idi && j < i)) ? 1 : 0;
+      }
+    }
+    if (rank < k) {
+      scores_out[static_cast<size_t>(row) * k + rank] = s[i];
+      ids_out[static_cast<size_t>(row) * k + rank] = id[i];
+    }
+  }
+}
+
+// all-pairs ranking for rows longer than PAIRS_LMAX (e.g. the merge of eight shards' top-256 lists): any L, O(L^2 / 32)
+// comparisons per lane
+__global__ void pairs_select_allpairs_kernel(int Q, int L, int k, const float* __restrict__ scores,
+                                             const long long* __restrict__ ids, float* __restrict__ scores_out,
+                                             long long* __restrict__ ids_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= Q) return;
+  const float* s = scores + static_cast<size_t>(row) * L;
+  const long long* id = ids + static_cast<size_t>(row) * L;
   for (int i = lane; i < L; i += 32) {
     const float si = s[i];
     const long long idi = id[i];
