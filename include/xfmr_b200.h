@@ -188,6 +188,8 @@ int xb_retrieval_metrics(int32_t num_queries, int32_t k, int32_t num_targets, co
  * `NOT IN (exclude_item_ids)` prefilter of data/lightning.py:247-252 (row_ids0 = NULL).
  * mask   : [ceil(num_rows/128)*128][xb_mask_words(num_cols)]      (bits for c >= num_cols are set)
  * mask_t : [ceil(num_cols/128)*128][xb_mask_words(num_rows)] or NULL (transposed copy)
+ * Ids are any int64 except INT64_MIN (the empty-slot key of the builder's hash table); that goes for item_idx / pos_idx of
+ * xb_loss_forward too, which builds its mask with the same kernels.
  * ---------------------------------------------------------------------------------------------- */
 size_t xb_pair_mask_workspace_bytes(int32_t num_cols);
 int xb_build_pair_mask(int32_t num_rows, int32_t num_cols, int32_t list_len, const int64_t* col_ids,
