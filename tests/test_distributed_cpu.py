@@ -172,14 +172,14 @@ def test_shard_local_exclusions_equal_the_global_prefilter() -> None:
     assert all(out[r] for r in range(world))
 
 
-def _retrieval_grid_worker(rank: int, world: int, port: int, out: dict) -> None:
+def _retrieval_grid_worker(rank: int, world: int, port: int, out: dict, nq: int = 10) -> None:
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import xfmr_b200  # noqa: PLC0415
     from oracle import native  # noqa: PLC0415
 
     rng = np.random.default_rng(5)
-    queries = rng.standard_normal((10, 16)).astype(np.float32)   # 2 query groups x 5 rows -> padded to 6 per group
+    queries = rng.standard_normal((nq, 16)).astype(np.float32)   # 10: 2 query groups x 5 rows -> padded to 6 per group
     catalog = rng.standard_normal((97, 16)).astype(np.float32)
     catalog[60] = catalog[3]                        # a tie across shards: the lower id must win
     grid = xfmr_b200.distributed.RetrievalGrid(2)   # 4 ranks = 2 catalog shards x 2 query groups
@@ -206,10 +206,11 @@ def _retrieval_grid_worker(rank: int, world: int, port: int, out: dict) -> None:
     dist.destroy_process_group()
 
 
-def test_retrieval_grid_two_shards_by_two_query_groups() -> None:
+@pytest.mark.parametrize("nq", [10, 3, 1])   # 3 and 1: the second query group is short / empty (all padding)
+def test_retrieval_grid_two_shards_by_two_query_groups(nq: int) -> None:
     """2-D layout (catalog shards x query groups) on 4 gloo ranks equals the unsharded search, ties and padding included."""
     world = 4
     manager = mp.Manager()
     out = manager.dict()
-    mp.spawn(_retrieval_grid_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_retrieval_grid_worker, args=(world, _free_port(), out, nq), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
