@@ -18,9 +18,10 @@
  *     mask builder on a library-owned helper stream that forks from `stream` and joins back into it with
  *     events before the call returns to it, also on every error return (XB_FORK=0 keeps everything on `stream`);
  *   - Threading: entry points are re-entrant; any number of host threads may call them concurrently on the same
- *     or different devices / streams.  The helper stream and its events are per host thread and device, so a
- *     thread that is capturing a CUDA graph pulls only its own helper stream into the capture and never sees
- *     work enqueued by another thread.  A workspace belongs to one call sequence (forward, then its backward)
+ *     or different devices / streams.  The helper streams and their events are per host thread and device, so a
+ *     thread that is capturing a CUDA graph pulls only its own helper streams into the capture and never sees
+ *     work enqueued by another thread (two non-blocking streams and four events per host thread and device, created
+ *     on first use and kept until the process exits).  A workspace belongs to one call sequence (forward, then its backward)
  *     at a time; xb_last_error_string() and the debug / timing hooks (xb_debug_*, xb_sweep_timing*) are the
  *     only per-thread / process-wide state;
  *   - return value: 0 = ok, < 0 = error code below; xb_last_error_string() describes the last failure on
