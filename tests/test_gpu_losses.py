@@ -100,6 +100,8 @@ def test_reference_golden_bf16_io(name: str) -> None:
     (129, 257, 64, 4, 0, 2.0, 0.5, True, True),       # one past the tile edge in both directions
     (300, 2000, 128, 16, 0, 10.0, 0.2, True, True),   # several column chunks
     (300, 2000, 128, 16, 8, 10.0, 0.2, False, True),  # mining across chunks
+    (300, 9000, 64, 8, 64, 4.0, 0.3, True, True),     # mining at the largest supported K, signed targets, ragged tiles
+    (30, 70, 32, 2, 64, 2.0, 0.5, False, True),       # K close to N: nearly every column is kept
     (64, 1500, 96, 8, 0, 1.0, 1.0, False, False),     # un-normalised embeddings exercise the norm terms
     (256, 700, 40, 40, 0, 30.0, -1.0, True, True),    # P > N/20, large sigma, negative margin
     (100, 32768, 32, 4, 0, 2.0, 0.5, False, True),    # one query row block: 64 column chunks (> one factor per lane)
