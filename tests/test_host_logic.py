@@ -278,3 +278,16 @@ def test_shim_submodules_are_the_loaded_modules() -> None:
     assert _loss_fwd is xfmr_b200.losses._loss_fwd  # noqa: SLF001
     for sub in ("losses", "retrieval", "hashing", "synthetic", "graphs", "distributed", "uniformity", "_lib"):
         assert importlib.import_module(f"xfmr_b200.{sub}") is sys.modules[f"matrix-factorization-torch_b200.{sub}"]
+
+
+def test_committed_ncu_traffic_has_the_keys_bench_reads() -> None:
+    """``bench.py`` fills ``roofline.traffic`` from ``profiles/ncu_traffic.json``: a renamed key would silently turn into null."""
+    import json  # noqa: PLC0415
+    import pathlib  # noqa: PLC0415
+    import re  # noqa: PLC0415
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    keys = set(re.findall(r'ncu_traffic\("([a-z_]+)"\)', (root / "bench.py").read_text()))
+    data = json.loads((root / "profiles" / "ncu_traffic.json").read_text())
+    assert keys and keys <= set(data), keys - set(data)
+    assert all(float(data[k]) > 0 for k in keys)
